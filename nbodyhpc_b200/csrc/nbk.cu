@@ -1,0 +1,520 @@
+// libnbk.so -- C ABI (include/nbk.h) over the sm_100a build and query kernels.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "common.cuh"
+#include "knn_query.cuh"
+#include "radix_sort.cuh"
+#include "tree_build.cuh"
+
+namespace nbk {
+std::atomic<uint64_t> g_launches{0};
+thread_local std::string g_error;
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int device) {
+        NBK_CUDA(cudaGetDevice(&prev));
+        if (device >= 0 && device != prev) NBK_CUDA(cudaSetDevice(device));
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+constexpr uint64_t kAlign = 256;
+
+struct ArenaLayout {
+    uint64_t nodes, x, y, z, idx, total;
+};
+
+inline ArenaLayout arena_layout(uint64_t n_padded, uint64_t n_nodes) {
+    ArenaLayout l;
+    uint64_t col = align_up(std::max<uint64_t>(n_padded, 1) * 4, kAlign);
+    l.nodes = 0;
+    l.x = align_up(n_nodes * sizeof(nbk_node), kAlign);
+    l.y = l.x + col;
+    l.z = l.y + col;
+    l.idx = l.z + col;
+    l.total = l.idx + col;
+    return l;
+}
+} // namespace nbk
+
+struct nbk_tree {
+    nbk_tree_meta meta{};
+    int device = 0;
+    char *arena = nullptr;
+    nbk::TreeArena view{};
+
+    void bind() {
+        nbk::ArenaLayout l = nbk::arena_layout(meta.n_padded, meta.n_nodes);
+        view.nodes = reinterpret_cast<nbk_node *>(arena + l.nodes);
+        view.x = reinterpret_cast<float *>(arena + l.x);
+        view.y = reinterpret_cast<float *>(arena + l.y);
+        view.z = reinterpret_cast<float *>(arena + l.z);
+        view.idx = reinterpret_cast<uint32_t *>(arena + l.idx);
+    }
+    // periodic < 0: the tree's own metric
+    nbk::QueryTree query_view(int periodic = -1, float box_size = 0.0f) const {
+        if (periodic < 0) {
+            periodic = meta.periodic;
+            box_size = meta.box_size;
+        }
+        nbk::QueryTree q;
+        q.nodes = view.nodes;
+        q.x = view.x;
+        q.y = view.y;
+        q.z = view.z;
+        q.idx = view.idx;
+        q.periodic = periodic != 0;
+        q.box = periodic ? box_size : 0.0f;
+        for (int d = 0; d < 3; ++d) {
+            // initial_box: kdtree.hpp:51-61 (open) / :111-120 (periodic)
+            q.lo[d] = periodic ? 0.0f : -FLT_MAX;
+            q.hi[d] = periodic ? box_size : FLT_MAX;
+        }
+        return q;
+    }
+};
+
+namespace nbk {
+
+template <typename F> int guarded(F &&f) {
+    try {
+        f();
+        return NBK_OK;
+    } catch (Error const &e) {
+        g_error = e.what();
+        return e.code;
+    } catch (std::bad_alloc const &) {
+        g_error = "host allocation failed";
+        return NBK_ERR_NOMEM;
+    } catch (std::exception const &e) {
+        g_error = e.what();
+        return NBK_ERR_INVALID;
+    }
+}
+
+void require_sm100(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        throw Error(NBK_ERR_CUDA, std::string("no CUDA device available (libnbk has no CPU fallback): ") +
+                                      cudaGetErrorString(e));
+    int dev = device;
+    if (dev < 0) NBK_CUDA(cudaGetDevice(&dev));
+    if (dev >= count) throw Error(NBK_ERR_INVALID, "device index out of range");
+    int major = 0;
+    NBK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10)
+        throw Error(NBK_ERR_CUDA, "libnbk is built for sm_100a only (compute capability 10.x required)");
+    // keep stream-ordered scratch memory cached in the pool instead of returning it at every sync
+    static std::atomic<uint64_t> pool_ready{0};
+    if (dev < 64 && !(pool_ready.load() & (1ull << dev))) {
+        cudaMemPool_t pool;
+        NBK_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t threshold = UINT64_MAX;
+        NBK_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+        pool_ready.fetch_or(1ull << dev);
+    }
+}
+
+void check_build_args(uint64_t n_padded, int block_size, bool soa) {
+    // kdtree.cpp:98-108, same order and wording
+    if (n_padded > 0xFFFFFFFFull) throw Error(NBK_ERR_INVALID, "More than uint32_t points are not supported.");
+    if (block_size <= 0 || block_size % 8 != 0) throw Error(NBK_ERR_INVALID, "block_size must be a multiple of 8.");
+    if (soa && n_padded % (uint64_t)block_size != 0)
+        throw Error(NBK_ERR_INVALID, "block_size must divide the number of points.");
+}
+
+std::unique_ptr<nbk_tree> alloc_tree(nbk_tree_meta const &meta, int device) {
+    auto t = std::make_unique<nbk_tree>();
+    t->meta = meta;
+    NBK_CUDA(cudaGetDevice(&t->device));
+    (void)device;
+    ArenaLayout l = arena_layout(meta.n_padded, meta.n_nodes);
+    t->meta.arena_bytes = l.total;
+    NBK_CUDA(cudaMalloc(&t->arena, l.total));
+    t->bind();
+    return t;
+}
+
+// Common tail of the three build entry points.  (x0,y0,z0[,idx0]) are device SoA columns of
+// n_padded points, perm holds the identity, bounds6 the orderable bounding box.
+std::unique_ptr<nbk_tree> finish_build(uint64_t n, uint64_t n_padded, int leaf_size, int block_size,
+                                       int periodic, float box_size, const float *x0,
+                                       const float *y0, const float *z0, const uint32_t *idx0,
+                                       uint32_t *perm, const uint32_t *d_bounds6, int device,
+                                       cudaStream_t stream) {
+    TopologyPlan plan = plan_topology(n_padded, leaf_size, block_size);
+    nbk_tree_meta meta{};
+    meta.n_points = n;
+    meta.n_padded = n_padded;
+    meta.n_nodes = plan.nodes.size();
+    meta.leaf_size = leaf_size;
+    meta.block_size = block_size;
+    meta.periodic = periodic ? 1 : 0;
+    meta.box_size = periodic ? box_size : 0.0f;
+    meta.n_levels = (int)plan.levels.size();
+    auto tree = alloc_tree(meta, device);
+    build_levels(plan, n_padded, x0, y0, z0, idx0, perm, tree->view, stream);
+    uint32_t b[6];
+    NBK_CUDA(cudaMemcpyAsync(b, d_bounds6, sizeof b, cudaMemcpyDeviceToHost, stream));
+    NBK_CUDA(cudaStreamSynchronize(stream));
+    for (int d = 0; d < 3; ++d) {
+        bool empty = b[d] == 0xFFFFFFFFu && b[3 + d] == 0u;
+        uint32_t lo = ordered_to_float(b[d]), hi = ordered_to_float(b[3 + d]);
+        std::memcpy(&tree->meta.lo[d], &lo, 4);
+        std::memcpy(&tree->meta.hi[d], &hi, 4);
+        if (empty) tree->meta.lo[d] = tree->meta.hi[d] = 0.0f;
+    }
+    return tree;
+}
+
+std::unique_ptr<nbk_tree> build_from_device_aos(const float *d_aos, uint64_t n, int leaf_size,
+                                                int block_size, int periodic, float box_size,
+                                                int device, cudaStream_t stream) {
+    check_build_args(n, block_size, false);
+    uint64_t n_padded = div_up(n, block_size) * block_size; // pybind.cpp:23
+    check_build_args(n_padded, block_size, false);
+    Scratch scratch(stream);
+    uint64_t cols = std::max<uint64_t>(n_padded, 1);
+    float *x0 = scratch.get<float>(cols), *y0 = scratch.get<float>(cols), *z0 = scratch.get<float>(cols);
+    uint32_t *perm = scratch.get<uint32_t>(cols);
+    uint32_t *aux = scratch.get<uint32_t>(8); // [0] flags, [1..6] bounds
+    const uint32_t init[8] = {0u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u, 0u};
+    NBK_CUDA(cudaMemcpyAsync(aux, init, sizeof init, cudaMemcpyHostToDevice, stream));
+    if (n_padded) {
+        ingest_aos_kernel<<<(unsigned)div_up(n_padded, 256), 256, 0, stream>>>(
+            d_aos, n, n_padded, x0, y0, z0, perm, periodic, box_size, aux, aux + 1);
+        NBK_LAUNCHED();
+    }
+    uint32_t flags = 0;
+    NBK_CUDA(cudaMemcpyAsync(&flags, aux, 4, cudaMemcpyDeviceToHost, stream));
+    NBK_CUDA(cudaStreamSynchronize(stream));
+    if (flags & 1u) // pybind.cpp:42-46
+        throw Error(NBK_ERR_INVALID, "When using periodic boundary conditions, all points must be "
+                                     "within the box (0 <= x <= box_size).");
+    return finish_build(n, n_padded, leaf_size, block_size, periodic, box_size, x0, y0, z0, nullptr,
+                        perm, aux + 1, device, stream);
+}
+
+// ---- query -----------------------------------------------------------------------------------------
+template <int K, bool P>
+void launch_packet(QueryTree const &qt, const float *d_q, const uint32_t *order, uint64_t m, int k,
+                   float *d_out_d, uint32_t *d_out_i, cudaStream_t stream) {
+    unsigned grid = (unsigned)div_up(m, kQueryThreads);
+    knn_packet_kernel<K, P><<<grid, kQueryThreads, 0, stream>>>(qt, d_q, order, m, k, d_out_d, d_out_i);
+    NBK_LAUNCHED();
+}
+
+template <bool P>
+void dispatch_packet(QueryTree const &qt, const float *d_q, const uint32_t *order, uint64_t m, int k,
+                     float *d_out_d, uint32_t *d_out_i, cudaStream_t stream) {
+    if (k <= 1) launch_packet<1, P>(qt, d_q, order, m, k, d_out_d, d_out_i, stream);
+    else if (k <= 2) launch_packet<2, P>(qt, d_q, order, m, k, d_out_d, d_out_i, stream);
+    else if (k <= 4) launch_packet<4, P>(qt, d_q, order, m, k, d_out_d, d_out_i, stream);
+    else if (k <= 8) launch_packet<8, P>(qt, d_q, order, m, k, d_out_d, d_out_i, stream);
+    else if (k <= 16) launch_packet<16, P>(qt, d_q, order, m, k, d_out_d, d_out_i, stream);
+    else if (k <= 32) launch_packet<32, P>(qt, d_q, order, m, k, d_out_d, d_out_i, stream);
+    else launch_packet<64, P>(qt, d_q, order, m, k, d_out_d, d_out_i, stream);
+}
+
+constexpr int kMaxK = 64;
+
+void query_device(nbk_tree const &tree, const float *d_q, uint64_t m, int k, float *d_out_d,
+                  uint32_t *d_out_i, cudaStream_t stream, int periodic = -1, float box_size = 0.0f) {
+    if (k <= 0) throw Error(NBK_ERR_INVALID, "k must be positive integer"); // pybind.cpp:92-94
+    if (k > kMaxK) throw Error(NBK_ERR_INVALID, "k > 64 is not supported by this build");
+    if (m == 0) return;
+    if (m > 0xFFFFFFFFull) throw Error(NBK_ERR_INVALID, "more than 2^32-1 queries per call");
+    Scratch scratch(stream);
+    uint32_t *keys_a = scratch.get<uint32_t>(m), *keys_b = scratch.get<uint32_t>(m);
+    uint32_t *vals_a = scratch.get<uint32_t>(m), *vals_b = scratch.get<uint32_t>(m);
+    uint32_t *work = scratch.get<uint32_t>(rs::sort_workspace_entries<uint32_t>(m));
+    // Morton grid over the box (periodic) or the points' bounding box (open)
+    float lo[3], scale[3];
+    QueryTree qt = tree.query_view(periodic, box_size);
+    for (int d = 0; d < 3; ++d) {
+        float l = qt.periodic ? 0.0f : tree.meta.lo[d];
+        float h = qt.periodic ? qt.box : tree.meta.hi[d];
+        float ext = h - l;
+        lo[d] = l;
+        scale[d] = (ext > 0.0f && std::isfinite(ext)) ? 1024.0f / ext : 0.0f;
+    }
+    morton_keys_kernel<<<(unsigned)div_up(m, 256), 256, 0, stream>>>(d_q, m, lo[0], lo[1], lo[2],
+                                                                   scale[0], scale[1], scale[2],
+                                                                   keys_a, vals_a);
+    NBK_LAUNCHED();
+    int where = rs::sort_pairs<uint32_t>(keys_a, vals_a, keys_b, vals_b, m, 0, 30, work, stream);
+    const uint32_t *order = where ? vals_b : vals_a;
+    if (qt.periodic) dispatch_packet<true>(qt, d_q, order, m, k, d_out_d, d_out_i, stream);
+    else dispatch_packet<false>(qt, d_q, order, m, k, d_out_d, d_out_i, stream);
+}
+
+} // namespace nbk
+
+using namespace nbk;
+
+extern "C" {
+
+const char *nbk_last_error(void) { return g_error.c_str(); }
+
+uint64_t nbk_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int nbk_device_count(void) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess) {
+        g_error = cudaGetErrorString(e);
+        return -1;
+    }
+    return count;
+}
+
+nbk_tree *nbk_tree_build(const float *xyz_aos, uint64_t n, int leaf_size, int block_size,
+                         int periodic, float box_size, int device, int *status) {
+    nbk_tree *out = nullptr;
+    int st = guarded([&] {
+        check_build_args(n, block_size, false);
+        require_sm100(device);
+        DeviceGuard guard(device);
+        cudaStream_t stream = nullptr; // legacy default stream
+        float *d_aos = nullptr;
+        NBK_CUDA(cudaMalloc(&d_aos, std::max<uint64_t>(n, 1) * 12));
+        std::unique_ptr<nbk_tree> tree;
+        try {
+            NBK_CUDA(cudaMemcpyAsync(d_aos, xyz_aos, n * 12, cudaMemcpyHostToDevice, stream));
+            tree = build_from_device_aos(d_aos, n, leaf_size, block_size, periodic, box_size, device,
+                                         stream);
+        } catch (...) {
+            cudaFree(d_aos);
+            throw;
+        }
+        cudaFree(d_aos);
+        out = tree.release();
+    });
+    if (status) *status = st;
+    return out;
+}
+
+nbk_tree *nbk_tree_build_device(const float *d_xyz_aos, uint64_t n, int leaf_size, int block_size,
+                                int periodic, float box_size, int device, void *stream,
+                                int *status) {
+    nbk_tree *out = nullptr;
+    int st = guarded([&] {
+        check_build_args(n, block_size, false);
+        require_sm100(device);
+        DeviceGuard guard(device);
+        out = build_from_device_aos(d_xyz_aos, n, leaf_size, block_size, periodic, box_size, device,
+                                    static_cast<cudaStream_t>(stream))
+                  .release();
+    });
+    if (status) *status = st;
+    return out;
+}
+
+nbk_tree *nbk_tree_build_soa(const float *x, const float *y, const float *z, const uint32_t *idx,
+                             uint64_t n_padded, int leaf_size, int block_size, int periodic,
+                             float box_size, int device, int *status) {
+    nbk_tree *out = nullptr;
+    int st = guarded([&] {
+        check_build_args(n_padded, block_size, true);
+        require_sm100(device);
+        DeviceGuard guard(device);
+        cudaStream_t stream = nullptr;
+        Scratch scratch(stream);
+        uint64_t cols = std::max<uint64_t>(n_padded, 1);
+        float *x0 = scratch.get<float>(cols), *y0 = scratch.get<float>(cols), *z0 = scratch.get<float>(cols);
+        uint32_t *idx0 = scratch.get<uint32_t>(cols), *perm = scratch.get<uint32_t>(cols);
+        uint32_t *aux = scratch.get<uint32_t>(8);
+        const uint32_t init[8] = {0u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u, 0u};
+        NBK_CUDA(cudaMemcpyAsync(aux, init, sizeof init, cudaMemcpyHostToDevice, stream));
+        NBK_CUDA(cudaMemcpyAsync(x0, x, n_padded * 4, cudaMemcpyHostToDevice, stream));
+        NBK_CUDA(cudaMemcpyAsync(y0, y, n_padded * 4, cudaMemcpyHostToDevice, stream));
+        NBK_CUDA(cudaMemcpyAsync(z0, z, n_padded * 4, cudaMemcpyHostToDevice, stream));
+        NBK_CUDA(cudaMemcpyAsync(idx0, idx, n_padded * 4, cudaMemcpyHostToDevice, stream));
+        if (n_padded) {
+            scan_soa_kernel<<<(unsigned)div_up(n_padded, 256), 256, 0, stream>>>(x0, y0, z0, n_padded,
+                                                                               perm, aux + 1);
+            NBK_LAUNCHED();
+        }
+        out = finish_build(n_padded, n_padded, leaf_size, block_size, periodic, box_size, x0, y0, z0,
+                           idx0, perm, aux + 1, device, stream)
+                  .release();
+    });
+    if (status) *status = st;
+    return out;
+}
+
+void nbk_tree_free(nbk_tree *tree) {
+    if (!tree) return;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(tree->device);
+    cudaFree(tree->arena);
+    if (prev >= 0) cudaSetDevice(prev);
+    delete tree;
+}
+
+int nbk_tree_get_meta(const nbk_tree *tree, nbk_tree_meta *meta) {
+    return guarded([&] {
+        if (!tree || !meta) throw Error(NBK_ERR_INVALID, "null argument");
+        *meta = tree->meta;
+    });
+}
+
+int nbk_tree_device(const nbk_tree *tree) { return tree ? tree->device : -1; }
+
+int nbk_tree_copy_nodes(const nbk_tree *tree, nbk_node *nodes) {
+    return guarded([&] {
+        if (!tree || !nodes) throw Error(NBK_ERR_INVALID, "null argument");
+        DeviceGuard guard(tree->device);
+        NBK_CUDA(cudaMemcpy(nodes, tree->view.nodes, tree->meta.n_nodes * sizeof(nbk_node),
+                            cudaMemcpyDeviceToHost));
+    });
+}
+
+int nbk_tree_copy_points(const nbk_tree *tree, float *x, float *y, float *z, uint32_t *idx) {
+    return guarded([&] {
+        if (!tree) throw Error(NBK_ERR_INVALID, "null argument");
+        DeviceGuard guard(tree->device);
+        uint64_t bytes = tree->meta.n_padded * 4;
+        if (x) NBK_CUDA(cudaMemcpy(x, tree->view.x, bytes, cudaMemcpyDeviceToHost));
+        if (y) NBK_CUDA(cudaMemcpy(y, tree->view.y, bytes, cudaMemcpyDeviceToHost));
+        if (z) NBK_CUDA(cudaMemcpy(z, tree->view.z, bytes, cudaMemcpyDeviceToHost));
+        if (idx) NBK_CUDA(cudaMemcpy(idx, tree->view.idx, bytes, cudaMemcpyDeviceToHost));
+    });
+}
+
+int nbk_tree_query_device(const nbk_tree *tree, const float *d_q_aos, uint64_t m, int k,
+                          float *d_out_dist, uint32_t *d_out_idx, void *stream) {
+    return guarded([&] {
+        if (!tree) throw Error(NBK_ERR_INVALID, "null argument");
+        DeviceGuard guard(tree->device);
+        query_device(*tree, d_q_aos, m, k, d_out_dist, d_out_idx, static_cast<cudaStream_t>(stream));
+    });
+}
+
+int nbk_tree_query(const nbk_tree *tree, const float *q_aos, uint64_t m, int k, float *out_dist,
+                   uint32_t *out_idx) {
+    return nbk_tree_query_ex(tree, q_aos, m, k, -1, 0.0f, out_dist, out_idx);
+}
+
+int nbk_tree_query_ex(const nbk_tree *tree, const float *q_aos, uint64_t m, int k, int periodic,
+                      float box_size, float *out_dist, uint32_t *out_idx) {
+    return guarded([&] {
+        if (!tree) throw Error(NBK_ERR_INVALID, "null argument");
+        if (k <= 0) throw Error(NBK_ERR_INVALID, "k must be positive integer");
+        if (k > kMaxK) throw Error(NBK_ERR_INVALID, "k > 64 is not supported by this build");
+        if (m == 0) return;
+        DeviceGuard guard(tree->device);
+        // Two chunks in flight: chunk c+1 uploads/computes while chunk c downloads.
+        const uint64_t chunk = std::min<uint64_t>(m, 1ull << 22);
+        cudaStream_t streams[2];
+        float *d_q[2] = {nullptr, nullptr}, *d_d[2] = {nullptr, nullptr};
+        uint32_t *d_i[2] = {nullptr, nullptr};
+        for (int s = 0; s < 2; ++s) NBK_CUDA(cudaStreamCreateWithFlags(&streams[s], cudaStreamNonBlocking));
+        auto cleanup = [&] {
+            for (int s = 0; s < 2; ++s) {
+                cudaStreamSynchronize(streams[s]);
+                cudaFree(d_q[s]);
+                cudaFree(d_d[s]);
+                cudaFree(d_i[s]);
+                cudaStreamDestroy(streams[s]);
+            }
+        };
+        try {
+            int nbuf = m > chunk ? 2 : 1;
+            for (int s = 0; s < nbuf; ++s) {
+                NBK_CUDA(cudaMalloc(&d_q[s], chunk * 12));
+                NBK_CUDA(cudaMalloc(&d_d[s], chunk * (uint64_t)k * 4));
+                NBK_CUDA(cudaMalloc(&d_i[s], chunk * (uint64_t)k * 4));
+            }
+            int s = 0;
+            for (uint64_t begin = 0; begin < m; begin += chunk, s ^= (nbuf - 1)) {
+                uint64_t cnt = std::min(chunk, m - begin);
+                cudaStream_t st = streams[s];
+                NBK_CUDA(cudaMemcpyAsync(d_q[s], q_aos + begin * 3, cnt * 12, cudaMemcpyHostToDevice, st));
+                query_device(*tree, d_q[s], cnt, k, d_d[s], d_i[s], st, periodic, box_size);
+                NBK_CUDA(cudaMemcpyAsync(out_dist + begin * k, d_d[s], cnt * (uint64_t)k * 4,
+                                         cudaMemcpyDeviceToHost, st));
+                NBK_CUDA(cudaMemcpyAsync(out_idx + begin * k, d_i[s], cnt * (uint64_t)k * 4,
+                                         cudaMemcpyDeviceToHost, st));
+            }
+            for (int t = 0; t < 2; ++t) NBK_CUDA(cudaStreamSynchronize(streams[t]));
+        } catch (...) {
+            cleanup();
+            throw;
+        }
+        cleanup();
+    });
+}
+
+int nbk_tree_stats(const nbk_tree *tree, const float *q_aos, uint64_t m, int k, int periodic,
+                   float box_size, uint64_t *out3) {
+    return guarded([&] {
+        if (!tree || !out3) throw Error(NBK_ERR_INVALID, "null argument");
+        if (k <= 0) throw Error(NBK_ERR_INVALID, "k must be positive integer");
+        if (k > kStatsMaxK) throw Error(NBK_ERR_INVALID, "k > 64 is not supported by this build");
+        out3[0] = out3[1] = out3[2] = 0;
+        if (m == 0) return;
+        DeviceGuard guard(tree->device);
+        cudaStream_t stream = nullptr;
+        Scratch scratch(stream);
+        float *d_q = scratch.get<float>(m * 3);
+        unsigned long long *d_out = scratch.get<unsigned long long>(3);
+        NBK_CUDA(cudaMemcpyAsync(d_q, q_aos, m * 12, cudaMemcpyHostToDevice, stream));
+        NBK_CUDA(cudaMemsetAsync(d_out, 0, 24, stream));
+        QueryTree qt = tree->query_view(periodic, box_size);
+        unsigned grid = (unsigned)div_up(m, 128);
+        if (qt.periodic) stats_kernel<true><<<grid, 128, 0, stream>>>(qt, d_q, m, k, d_out);
+        else stats_kernel<false><<<grid, 128, 0, stream>>>(qt, d_q, m, k, d_out);
+        NBK_LAUNCHED();
+        unsigned long long h[3];
+        NBK_CUDA(cudaMemcpyAsync(h, d_out, 24, cudaMemcpyDeviceToHost, stream));
+        NBK_CUDA(cudaStreamSynchronize(stream));
+        for (int c = 0; c < 3; ++c) out3[c] = h[c];
+    });
+}
+
+int nbk_tree_arena(const nbk_tree *tree, void **d_arena, uint64_t *bytes) {
+    return guarded([&] {
+        if (!tree) throw Error(NBK_ERR_INVALID, "null argument");
+        if (d_arena) *d_arena = tree->arena;
+        if (bytes) *bytes = tree->meta.arena_bytes;
+    });
+}
+
+nbk_tree *nbk_tree_alloc_replica(const nbk_tree_meta *meta, int device, int *status) {
+    nbk_tree *out = nullptr;
+    int st = guarded([&] {
+        if (!meta) throw Error(NBK_ERR_INVALID, "null argument");
+        require_sm100(device);
+        DeviceGuard guard(device);
+        ArenaLayout l = arena_layout(meta->n_padded, meta->n_nodes);
+        if (meta->arena_bytes != l.total) throw Error(NBK_ERR_INVALID, "tree meta does not match this library's arena layout");
+        out = alloc_tree(*meta, device).release();
+    });
+    if (status) *status = st;
+    return out;
+}
+
+void *nbk_host_alloc(uint64_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        g_error = "cudaHostAlloc failed";
+        return nullptr;
+    }
+    return p;
+}
+
+void nbk_host_free(void *ptr) {
+    if (ptr) cudaFreeHost(ptr);
+}
+
+} // extern "C"

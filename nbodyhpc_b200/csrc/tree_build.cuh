@@ -1,0 +1,263 @@
+// kd-tree construction on the device.
+//
+// Replaces the reference's recursive builder + Floyd-Rivest/AVX2 selection
+// (kdtree_impl.hpp:94-157, kdtree_selection.cpp:34-200,322-368,475-494) with a level-synchronous
+// build.  The topology is a function of point COUNTS only (leaf iff count <= max(leaf, 2*block);
+// median_offset = ((count/2)/block)*block; kdtree_impl.hpp:91,101-110), so the host lays out every
+// node, segment boundary and split position up front (plan_topology) and the device only has to
+// order the points: per level one segmented radix sort by (segment, coordinate[level % 3]) moving a
+// permutation, after which the element at each segment's median position IS the rank-median_offset
+// element the reference selects, and its coordinate is the node's split.
+#pragma once
+
+#include <vector>
+
+#include "common.cuh"
+#include "radix_sort.cuh"
+
+namespace nbk {
+
+// ---- host-side topology plan ---------------------------------------------------------------------
+struct LevelPlan {
+    // indexed by segment id at this level (root = 0, children of s are 2s and 2s+1)
+    std::vector<uint32_t> mid;   // absolute position of the median element; UINT32_MAX = no split
+    std::vector<int32_t> node;   // node index receiving the split; -1 = no split
+};
+
+struct TopologyPlan {
+    std::vector<nbk_node> nodes; // pre-order, left subtree first; splits filled by the device
+    std::vector<LevelPlan> levels;
+};
+
+inline uint32_t plan_node(TopologyPlan &plan, uint64_t leaf, uint64_t block, int level,
+                          uint64_t seg, int dim, uint32_t left, uint32_t count) {
+    uint32_t me = (uint32_t)plan.nodes.size();
+    if (count <= leaf) { // kdtree_impl.hpp:101-105
+        plan.nodes.push_back(nbk_node{-1, 0.0f, left, left + count});
+        return me;
+    }
+    uint32_t median = (uint32_t)((count / 2 / block) * block); // kdtree_impl.hpp:108-110
+    plan.nodes.push_back(nbk_node{dim, 0.0f, 0u, 0u});
+    if ((int)plan.levels.size() <= level) plan.levels.resize(level + 1);
+    LevelPlan &lp = plan.levels[level];
+    if (lp.mid.empty()) {
+        lp.mid.assign((size_t)1 << level, 0xFFFFFFFFu);
+        lp.node.assign((size_t)1 << level, -1);
+    }
+    lp.mid[seg] = left + median;
+    lp.node[seg] = (int32_t)me;
+    uint32_t l = plan_node(plan, leaf, block, level + 1, 2 * seg, (dim + 1) % 3, left, median);
+    uint32_t r = plan_node(plan, leaf, block, level + 1, 2 * seg + 1, (dim + 1) % 3,
+                           left + median, count - median);
+    plan.nodes[me].left = l;
+    plan.nodes[me].right = r;
+    return me;
+}
+
+inline TopologyPlan plan_topology(uint64_t n_padded, int leaf_size, int block_size) {
+    TopologyPlan plan;
+    uint64_t leaf = (uint64_t)std::max(leaf_size, 2 * block_size); // kdtree_impl.hpp:91
+    plan_node(plan, leaf, (uint64_t)block_size, 0, 0, 0, 0u, (uint32_t)n_padded);
+    return plan;
+}
+
+// ---- kernels -------------------------------------------------------------------------------------
+
+// AoS (n,3) -> SoA columns padded with FLT_MAX to n_padded, identity permutation, segment 0
+// (pybind.cpp:14-56).  flags[0] |= 1 if a coordinate is outside [0, box] (periodic only);
+// bounds6 = {min x,y,z, max x,y,z} of the real points as orderable uint32.
+__global__ void __launch_bounds__(256)
+ingest_aos_kernel(const float *__restrict__ aos, uint64_t n, uint64_t n_padded,
+                  float *__restrict__ x, float *__restrict__ y, float *__restrict__ z,
+                  uint32_t *__restrict__ perm, int periodic, float box, uint32_t *flags,
+                  uint32_t *bounds6) {
+    __shared__ float tile[256 * 3];
+    uint64_t base = (uint64_t)blockIdx.x * 256;
+    uint64_t in_tile = n > base ? (n - base < 256 ? n - base : 256) : 0;
+    for (uint32_t j = threadIdx.x; j < in_tile * 3; j += 256) tile[j] = aos[base * 3 + j];
+    __syncthreads();
+    uint64_t i = base + threadIdx.x;
+    float px = FLT_MAX, py = FLT_MAX, pz = FLT_MAX;
+    bool real = i < n;
+    if (real) {
+        px = tile[threadIdx.x * 3];
+        py = tile[threadIdx.x * 3 + 1];
+        pz = tile[threadIdx.x * 3 + 2];
+    }
+    if (i < n_padded) {
+        x[i] = px;
+        y[i] = py;
+        z[i] = pz;
+        perm[i] = (uint32_t)i;
+    }
+    bool bad = real && periodic &&
+               !(px >= 0.0f && px <= box && py >= 0.0f && py <= box && pz >= 0.0f && pz <= box);
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flags, 1u);
+    // bounding box of the real points (warp reduce, then one atomic per warp)
+    uint32_t lo[3], hi[3];
+    const float p[3] = {px, py, pz};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        uint32_t o = float_to_ordered(__float_as_uint(p[d]));
+        lo[d] = real ? o : 0xFFFFFFFFu;
+        hi[d] = real ? o : 0u;
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            lo[d] = min(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], s));
+            hi[d] = max(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], s));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            if (lo[d] != 0xFFFFFFFFu) atomicMin(&bounds6[d], lo[d]);
+            if (hi[d] != 0u) atomicMax(&bounds6[3 + d], hi[d]);
+        }
+    }
+}
+
+// Bounding box + periodic validation for a tree handed over as SoA columns.
+__global__ void __launch_bounds__(256)
+scan_soa_kernel(const float *__restrict__ x, const float *__restrict__ y,
+                const float *__restrict__ z, uint64_t n, uint32_t *__restrict__ perm,
+                uint32_t *bounds6) {
+    uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    bool in = i < n;
+    float p[3] = {in ? x[i] : 0.f, in ? y[i] : 0.f, in ? z[i] : 0.f};
+    if (in) perm[i] = (uint32_t)i;
+    // padding points (FLT_MAX) do not belong to the bounding box
+    bool real = in && !(p[0] == FLT_MAX && p[1] == FLT_MAX && p[2] == FLT_MAX);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        uint32_t o = float_to_ordered(__float_as_uint(p[d]));
+        uint32_t lo = real ? o : 0xFFFFFFFFu, hi = real ? o : 0u;
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, s));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, s));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (lo != 0xFFFFFFFFu) atomicMin(&bounds6[d], lo);
+            if (hi != 0u) atomicMax(&bounds6[3 + d], hi);
+        }
+    }
+}
+
+// key[i] = (segment(i) << 32) | orderable(coord[perm[i]]).  seg_prev/mid_prev describe the level
+// above: an element of segment s goes to 2s (left of the median position) or 2s+1.
+__global__ void __launch_bounds__(256)
+make_keys_kernel(const float *__restrict__ coord, const uint32_t *__restrict__ perm,
+                 uint32_t *__restrict__ seg, const uint32_t *__restrict__ mid_prev, int level,
+                 uint64_t n, uint64_t *__restrict__ keys) {
+    uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s = 0;
+    if (level > 0) {
+        uint32_t sp = seg[i];
+        s = 2 * sp + ((uint32_t)i >= mid_prev[sp] ? 1u : 0u);
+    }
+    seg[i] = s;
+    uint32_t o = float_to_ordered(__float_as_uint(coord[perm[i]]));
+    keys[i] = ((uint64_t)s << 32) | o;
+}
+
+// nodes[node[s]].split = coordinate of the element now sitting at mid[s]
+__global__ void __launch_bounds__(256)
+record_splits_kernel(const uint64_t *__restrict__ sorted_keys, const uint32_t *__restrict__ mid,
+                     const int32_t *__restrict__ node, uint32_t nseg, nbk_node *__restrict__ nodes) {
+    uint32_t s = blockIdx.x * 256 + threadIdx.x;
+    if (s >= nseg) return;
+    int32_t nd = node[s];
+    if (nd < 0) return;
+    uint32_t o = (uint32_t)sorted_keys[mid[s]];
+    nodes[nd].split = __uint_as_float(ordered_to_float(o));
+}
+
+__global__ void __launch_bounds__(256)
+gather_points_kernel(const float *__restrict__ x0, const float *__restrict__ y0,
+                     const float *__restrict__ z0, const uint32_t *__restrict__ idx0,
+                     const uint32_t *__restrict__ perm, uint64_t n, float *__restrict__ x,
+                     float *__restrict__ y, float *__restrict__ z, uint32_t *__restrict__ idx) {
+    uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    uint32_t p = perm[i];
+    x[i] = x0[p];
+    y[i] = y0[p];
+    z[i] = z0[p];
+    idx[i] = idx0 ? idx0[p] : p;
+}
+
+// ---- driver --------------------------------------------------------------------------------------
+struct TreeArena {
+    nbk_node *nodes;
+    float *x, *y, *z;
+    uint32_t *idx;
+};
+
+// Orders the points held in (x0,y0,z0[,idx0]) into the arena and fills the node array.
+// perm must hold the identity on entry.
+inline void build_levels(TopologyPlan const &plan, uint64_t n_padded, const float *x0,
+                         const float *y0, const float *z0, const uint32_t *idx0, uint32_t *perm,
+                         TreeArena const &arena, cudaStream_t stream) {
+    const int n_levels = (int)plan.levels.size();
+    NBK_CUDA(cudaMemcpyAsync(arena.nodes, plan.nodes.data(), plan.nodes.size() * sizeof(nbk_node),
+                             cudaMemcpyHostToDevice, stream));
+    const unsigned grid = (unsigned)div_up(n_padded ? n_padded : 1, 256);
+    if (n_levels > 0) {
+        Scratch scratch(stream);
+        uint64_t *keys_a = scratch.get<uint64_t>(n_padded);
+        uint64_t *keys_b = scratch.get<uint64_t>(n_padded);
+        uint32_t *perm_b = scratch.get<uint32_t>(n_padded);
+        uint32_t *seg = scratch.get<uint32_t>(n_padded);
+        uint32_t *work = scratch.get<uint32_t>(rs::sort_workspace_entries<uint64_t>(n_padded));
+        // per-level segment tables, one upload
+        uint64_t table_entries = 0;
+        for (auto const &lp : plan.levels) table_entries += lp.mid.size();
+        std::vector<uint32_t> h_mid(table_entries);
+        std::vector<int32_t> h_node(table_entries);
+        std::vector<uint64_t> level_ofs(n_levels);
+        uint64_t ofs = 0;
+        for (int l = 0; l < n_levels; ++l) {
+            level_ofs[l] = ofs;
+            std::copy(plan.levels[l].mid.begin(), plan.levels[l].mid.end(), h_mid.begin() + ofs);
+            std::copy(plan.levels[l].node.begin(), plan.levels[l].node.end(), h_node.begin() + ofs);
+            ofs += plan.levels[l].mid.size();
+        }
+        uint32_t *d_mid = scratch.get<uint32_t>(table_entries);
+        int32_t *d_node = scratch.get<int32_t>(table_entries);
+        NBK_CUDA(cudaMemcpyAsync(d_mid, h_mid.data(), table_entries * 4, cudaMemcpyHostToDevice,
+                                 stream));
+        NBK_CUDA(cudaMemcpyAsync(d_node, h_node.data(), table_entries * 4, cudaMemcpyHostToDevice,
+                                 stream));
+        uint32_t *perm_cur = perm, *perm_alt = perm_b;
+        for (int l = 0; l < n_levels; ++l) {
+            const float *coord = (l % 3 == 0) ? x0 : ((l % 3 == 1) ? y0 : z0);
+            make_keys_kernel<<<grid, 256, 0, stream>>>(
+                coord, perm_cur, seg, l > 0 ? d_mid + level_ofs[l - 1] : nullptr, l, n_padded,
+                keys_a);
+            NBK_LAUNCHED();
+            int where = rs::sort_pairs<uint64_t>(keys_a, perm_cur, keys_b, perm_alt, n_padded, 0,
+                                                 32 + l, work, stream);
+            const uint64_t *sorted = where ? keys_b : keys_a;
+            if (where) std::swap(perm_cur, perm_alt);
+            uint32_t nseg = (uint32_t)plan.levels[l].mid.size();
+            record_splits_kernel<<<(unsigned)div_up(nseg, 256), 256, 0, stream>>>(
+                sorted, d_mid + level_ofs[l], d_node + level_ofs[l], nseg, arena.nodes);
+            NBK_LAUNCHED();
+        }
+        gather_points_kernel<<<grid, 256, 0, stream>>>(x0, y0, z0, idx0, perm_cur, n_padded,
+                                                       arena.x, arena.y, arena.z, arena.idx);
+        NBK_LAUNCHED();
+        // the host tables must outlive the async copies
+        NBK_CUDA(cudaStreamSynchronize(stream));
+    } else {
+        if (n_padded) {
+            gather_points_kernel<<<grid, 256, 0, stream>>>(x0, y0, z0, idx0, perm, n_padded,
+                                                           arena.x, arena.y, arena.z, arena.idx);
+            NBK_LAUNCHED();
+        }
+        NBK_CUDA(cudaStreamSynchronize(stream));
+    }
+}
+
+} // namespace nbk
