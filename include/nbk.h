@@ -94,6 +94,13 @@ NBK_API nbk_tree *nbk_tree_build_soa(const float *x, const float *y, const float
                                      int block_size, int periodic, float box_size, int device,
                                      int *status);
 
+/* Host-only: the tree topology the build will produce for n points (it is a function of counts
+ * only, kdtree_impl.hpp:91,101-110).  Writes n_nodes / n_levels and, if `nodes` is not NULL, the
+ * node records in the reference's pre-order with dim/left/right filled and split = 0.  Needs no
+ * GPU; backs the `size` property before/without a build and the host-logic tests. */
+NBK_API int nbk_plan_topology(uint64_t n_points, int leaf_size, int block_size, nbk_node *nodes,
+                              uint64_t *n_nodes, int *n_levels);
+
 NBK_API void nbk_tree_free(nbk_tree *tree);
 
 /* ---- introspection ------------------------------------------------------------------------ */
@@ -140,6 +147,18 @@ NBK_API int nbk_tree_arena(const nbk_tree *tree, void **d_arena, uint64_t *bytes
 /* Allocates an empty tree with the given meta on `device`; the caller fills its arena (e.g. as the
  * destination of ncclBroadcast) before querying it. */
 NBK_API nbk_tree *nbk_tree_alloc_replica(const nbk_tree_meta *meta, int device, int *status);
+
+/* ---- device-side timing of the library's own kernels (bench.py's roofline numbers) ---------- */
+enum { NBK_SECTION_QUERY_ORDER = 0, /* Morton keys + radix sort of the queries */
+       NBK_SECTION_KNN_KERNEL = 1,  /* the kNN traversal kernel                */
+       NBK_SECTION_COUNT = 2 };
+
+/* When enabled, every query brackets its sections with CUDA events on the launching stream. */
+NBK_API void nbk_profile_enable(int on);
+
+/* Waits for the recorded events, returns the summed duration (ms) and number of recordings of
+ * `section` since the last read, and resets it. */
+NBK_API int nbk_profile_read(int section, double *total_ms, uint64_t *count);
 
 /* ---- pinned host staging (optional; speeds up the host-buffer entry points) ---------------- */
 NBK_API void *nbk_host_alloc(uint64_t bytes);

@@ -19,11 +19,14 @@ NODE_DTYPE = np.dtype([("dim", np.int32), ("split", np.float32), ("left", np.uin
 # every symbol include/nbk.h declares (tests check that the library exports exactly these)
 SYMBOLS = [
     "nbk_last_error", "nbk_launch_count", "nbk_device_count",
-    "nbk_tree_build", "nbk_tree_build_device", "nbk_tree_build_soa", "nbk_tree_free",
+    "nbk_tree_build", "nbk_tree_build_device", "nbk_tree_build_soa", "nbk_plan_topology", "nbk_tree_free",
     "nbk_tree_get_meta", "nbk_tree_device", "nbk_tree_copy_nodes", "nbk_tree_copy_points",
     "nbk_tree_query", "nbk_tree_query_device", "nbk_tree_query_ex", "nbk_tree_stats",
-    "nbk_tree_arena", "nbk_tree_alloc_replica", "nbk_host_alloc", "nbk_host_free",
+    "nbk_tree_arena", "nbk_tree_alloc_replica", "nbk_profile_enable", "nbk_profile_read",
+    "nbk_host_alloc", "nbk_host_free",
 ]
+
+SECTION_QUERY_ORDER, SECTION_KNN_KERNEL = 0, 1
 
 
 class TreeMeta(C.Structure):
@@ -61,6 +64,7 @@ def lib() -> C.CDLL:
         L.nbk_tree_build_device.argtypes = [vp, u64, i32, i32, i32, f32, i32, vp, ip]
         L.nbk_tree_build_soa.restype = vp
         L.nbk_tree_build_soa.argtypes = [vp, vp, vp, vp, u64, i32, i32, i32, f32, i32, ip]
+        L.nbk_plan_topology.argtypes = [u64, i32, i32, vp, C.POINTER(u64), ip]
         L.nbk_tree_free.argtypes = [vp]
         L.nbk_tree_get_meta.argtypes = [vp, C.POINTER(TreeMeta)]
         L.nbk_tree_device.argtypes = [vp]
@@ -73,6 +77,8 @@ def lib() -> C.CDLL:
         L.nbk_tree_arena.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
         L.nbk_tree_alloc_replica.restype = vp
         L.nbk_tree_alloc_replica.argtypes = [C.POINTER(TreeMeta), i32, ip]
+        L.nbk_profile_enable.argtypes = [i32]
+        L.nbk_profile_read.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(u64)]
         L.nbk_host_alloc.restype = vp
         L.nbk_host_alloc.argtypes = [u64]
         L.nbk_host_free.argtypes = [vp]
@@ -93,6 +99,28 @@ def _check(status: int) -> None:
 
 def launch_count() -> int:
     return int(lib().nbk_launch_count())
+
+
+def plan_topology(n_points: int, leaf_size: int = 64, block_size: int = 8, with_nodes: bool = True):
+    """Host-only: (node records with split = 0, number of levels) the build will produce."""
+    n_nodes, n_levels = C.c_uint64(), C.c_int()
+    _check(lib().nbk_plan_topology(n_points, leaf_size, block_size, None, C.byref(n_nodes), C.byref(n_levels)))
+    nodes = None
+    if with_nodes:
+        nodes = np.empty(n_nodes.value, NODE_DTYPE)
+        _check(lib().nbk_plan_topology(n_points, leaf_size, block_size, _host_ptr(nodes), None, None))
+    return nodes, int(n_nodes.value), int(n_levels.value)
+
+
+def profile_enable(on: bool) -> None:
+    lib().nbk_profile_enable(int(on))
+
+
+def profile_read(section: int):
+    """(total milliseconds, recordings) of a section since the last read; waits for the events."""
+    ms, cnt = C.c_double(), C.c_uint64()
+    _check(lib().nbk_profile_read(section, C.byref(ms), C.byref(cnt)))
+    return ms.value, int(cnt.value)
 
 
 def _host_ptr(a: np.ndarray):

@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -203,6 +204,36 @@ std::unique_ptr<nbk_tree> build_from_device_aos(const float *d_aos, uint64_t n, 
                         perm, aux + 1, device, stream);
 }
 
+// ---- optional event timing of sections ------------------------------------------------------------
+std::atomic<int> g_profile{0};
+std::mutex g_profile_mutex;
+std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_profile_events[NBK_SECTION_COUNT];
+
+struct SectionTimer {
+    int section;
+    cudaStream_t stream;
+    cudaEvent_t start = nullptr, stop = nullptr;
+    SectionTimer(int sec, cudaStream_t s) : section(sec), stream(s) {
+        if (!g_profile.load(std::memory_order_relaxed)) return;
+        NBK_CUDA(cudaEventCreate(&start));
+        NBK_CUDA(cudaEventCreate(&stop));
+        NBK_CUDA(cudaEventRecord(start, stream));
+    }
+    void finish() {
+        if (!start) return;
+        NBK_CUDA(cudaEventRecord(stop, stream));
+        std::lock_guard<std::mutex> lock(g_profile_mutex);
+        g_profile_events[section].emplace_back(start, stop);
+        start = nullptr;
+    }
+    ~SectionTimer() {
+        if (start) {
+            cudaEventDestroy(start);
+            cudaEventDestroy(stop);
+        }
+    }
+};
+
 // ---- query -----------------------------------------------------------------------------------------
 template <int K, bool P>
 void launch_packet(QueryTree const &qt, const float *d_q, const uint32_t *order, uint64_t m, int k,
@@ -246,14 +277,18 @@ void query_device(nbk_tree const &tree, const float *d_q, uint64_t m, int k, flo
         lo[d] = l;
         scale[d] = (ext > 0.0f && std::isfinite(ext)) ? 1024.0f / ext : 0.0f;
     }
+    SectionTimer t_order(NBK_SECTION_QUERY_ORDER, stream);
     morton_keys_kernel<<<(unsigned)div_up(m, 256), 256, 0, stream>>>(d_q, m, lo[0], lo[1], lo[2],
                                                                    scale[0], scale[1], scale[2],
                                                                    keys_a, vals_a);
     NBK_LAUNCHED();
     int where = rs::sort_pairs<uint32_t>(keys_a, vals_a, keys_b, vals_b, m, 0, 30, work, stream);
     const uint32_t *order = where ? vals_b : vals_a;
+    t_order.finish();
+    SectionTimer t_knn(NBK_SECTION_KNN_KERNEL, stream);
     if (qt.periodic) dispatch_packet<true>(qt, d_q, order, m, k, d_out_d, d_out_i, stream);
     else dispatch_packet<false>(qt, d_q, order, m, k, d_out_d, d_out_i, stream);
+    t_knn.finish();
 }
 
 } // namespace nbk
@@ -349,6 +384,19 @@ nbk_tree *nbk_tree_build_soa(const float *x, const float *y, const float *z, con
     });
     if (status) *status = st;
     return out;
+}
+
+int nbk_plan_topology(uint64_t n_points, int leaf_size, int block_size, nbk_node *nodes,
+                      uint64_t *n_nodes, int *n_levels) {
+    return guarded([&] {
+        check_build_args(n_points, block_size, false);
+        uint64_t n_padded = div_up(n_points, block_size) * block_size;
+        check_build_args(n_padded, block_size, false);
+        TopologyPlan plan = plan_topology(n_padded, leaf_size, block_size);
+        if (n_nodes) *n_nodes = plan.nodes.size();
+        if (n_levels) *n_levels = (int)plan.levels.size();
+        if (nodes) std::copy(plan.nodes.begin(), plan.nodes.end(), nodes);
+    });
 }
 
 void nbk_tree_free(nbk_tree *tree) {
@@ -502,6 +550,30 @@ nbk_tree *nbk_tree_alloc_replica(const nbk_tree_meta *meta, int device, int *sta
     });
     if (status) *status = st;
     return out;
+}
+
+void nbk_profile_enable(int on) { g_profile.store(on ? 1 : 0); }
+
+int nbk_profile_read(int section, double *total_ms, uint64_t *count) {
+    return guarded([&] {
+        if (section < 0 || section >= NBK_SECTION_COUNT) throw Error(NBK_ERR_INVALID, "bad section");
+        std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+        {
+            std::lock_guard<std::mutex> lock(g_profile_mutex);
+            events.swap(g_profile_events[section]);
+        }
+        double total = 0.0;
+        for (auto &e : events) {
+            NBK_CUDA(cudaEventSynchronize(e.second));
+            float ms = 0.0f;
+            NBK_CUDA(cudaEventElapsedTime(&ms, e.first, e.second));
+            total += ms;
+            cudaEventDestroy(e.first);
+            cudaEventDestroy(e.second);
+        }
+        if (total_ms) *total_ms = total;
+        if (count) *count = events.size();
+    });
 }
 
 void *nbk_host_alloc(uint64_t bytes) {

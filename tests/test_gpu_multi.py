@@ -1,0 +1,56 @@
+"""Multi-GPU path on real devices: NCCL-broadcast replica answers byte-identically to the source
+tree.  Needs >= 2 GPUs (skipped otherwise); the host logic is covered on CPU by test_dist_gloo.py."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from helpers import philox
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from nbodyhpc_b200 import capi
+    from nbodyhpc_b200.dist import replicate_tree, shard_range
+
+    pts, q = philox(300_000, 42), philox(40_001, 43)
+    tree = capi.Tree.build(pts, 64, 1.0, device=rank) if rank == 0 else None
+    tree = replicate_tree(tree, src=0, device=rank)
+    b, e = shard_range(len(q), rank, world)
+    d, i = tree.query(q[b:e], 8)
+    np.savez(os.path.join(out_dir, f"shard{rank}.npz"), d=d, i=i, nodes=tree.nodes().view(np.uint8))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_replica_is_byte_identical_and_shards_compose(gpu, tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    pts, q = philox(300_000, 42), philox(40_001, 43)
+    tree = gpu.Tree.build(pts, 64, 1.0, device=0)
+    d_full, i_full = tree.query(q, 8)
+    shards = [np.load(tmp_path / f"shard{r}.npz") for r in range(world)]
+    for s in shards:
+        assert np.array_equal(s["nodes"], tree.nodes().view(np.uint8))
+    d = np.concatenate([s["d"] for s in shards])
+    i = np.concatenate([s["i"] for s in shards])
+    assert np.array_equal(d.view(np.uint32), d_full.view(np.uint32)) and np.array_equal(i, i_full)
