@@ -39,6 +39,10 @@ class TreeMeta(C.Structure):
 
 
 def library_path() -> str:
+    # NBK_LIBRARY: an alternative build of the same library (kernel-variant experiments)
+    override = os.environ.get("NBK_LIBRARY")
+    if override:
+        return override
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libnbk.so")
 
 

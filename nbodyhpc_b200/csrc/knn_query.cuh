@@ -78,12 +78,10 @@ __device__ __forceinline__ float axis_lb_open(float lo, float hi, float q) {
     return __fadd_rn(__fmul_rn(dl, dl), __fmul_rn(dr, dr));
 }
 
-// periodic metric: lower bound of min(d^2, (d+L)^2, (d-L)^2) over d = fl(p - q), p in [lo, hi].
-// `wrap` is set when some point of the cell may need a wrapped image for this query.
-__device__ __forceinline__ float axis_lb_periodic(float lo, float hi, float q, float L, float halfL,
-                                                  bool &wrap) {
-    float a = __fsub_rn(lo, q), b = __fsub_rn(hi, q); // d in [a, b]
-    wrap = wrap || (a < -halfL) || (b > halfL);
+// periodic metric: lower bound of min(d^2, (d+L)^2, (d-L)^2) over d = fl(p - q) in [a, b]
+// (a = fl(lo - q), b = fl(hi - q)): each image interval is the same monotone operation applied to
+// the end points, and the distance of an interval [u, v] from zero is max(u, -v, 0).
+__device__ __forceinline__ float axis_lb_periodic(float a, float b, float L) {
     float v0 = fmaxf(fmaxf(a, -b), 0.0f);
     float ap = __fadd_rn(a, L), bp = __fadd_rn(b, L);
     float vp = fmaxf(fmaxf(ap, -bp), 0.0f);
@@ -141,34 +139,51 @@ template <int K> struct TopK {
 };
 
 // ---- the packet kernel ------------------------------------------------------------------------------
-template <int K, bool PERIODIC>
+template <bool WRAP>
+__device__ __forceinline__ void leaf_d2x4(float4 const &X, float4 const &Y, float4 const &Z, float qx,
+                                          float qy, float qz, float L, float d[4]) {
+    if (WRAP) {
+        d[0] = d2_periodic(X.x, Y.x, Z.x, qx, qy, qz, L);
+        d[1] = d2_periodic(X.y, Y.y, Z.y, qx, qy, qz, L);
+        d[2] = d2_periodic(X.z, Y.z, Z.z, qx, qy, qz, L);
+        d[3] = d2_periodic(X.w, Y.w, Z.w, qx, qy, qz, L);
+    } else {
+        d[0] = d2_open(X.x, Y.x, Z.x, qx, qy, qz);
+        d[1] = d2_open(X.y, Y.y, Z.y, qx, qy, qz);
+        d[2] = d2_open(X.z, Y.z, Z.z, qx, qy, qz);
+        d[3] = d2_open(X.w, Y.w, Z.w, qx, qy, qz);
+    }
+}
+
+// One leaf for all 32 lanes.  Leaves start on multiples of 8 points and hold a multiple of 8
+// (block_size 8), so every step is three warp-uniform 16-byte loads (x, y, z of 4 points); the
+// loads of step i+1 are issued before the arithmetic of step i.
+template <int K, bool WRAP>
 __device__ __forceinline__ void scan_leaf(QueryTree const &t, uint32_t begin, uint32_t end, float qx,
-                                          float qy, float qz, bool wrap, TopK<K> &top) {
-    // leaves start on multiples of 8 points and hold a multiple of 8: two float4 per column/step
-    for (uint32_t p = begin; p < end; p += 4) {
-        const float4 X = __ldg(reinterpret_cast<const float4 *>(t.x + p));
-        const float4 Y = __ldg(reinterpret_cast<const float4 *>(t.y + p));
-        const float4 Z = __ldg(reinterpret_cast<const float4 *>(t.z + p));
+                                          float qy, float qz, TopK<K> &top) {
+    const float4 *px = reinterpret_cast<const float4 *>(t.x + begin);
+    const float4 *py = reinterpret_cast<const float4 *>(t.y + begin);
+    const float4 *pz = reinterpret_cast<const float4 *>(t.z + begin);
+    const uint32_t steps = (end - begin) >> 2;
+    float4 X = __ldg(px), Y = __ldg(py), Z = __ldg(pz);
+    for (uint32_t s = 0; s < steps; ++s) {
+        const uint32_t nxt = s + 1 < steps ? s + 1 : s;
+        const float4 Xn = __ldg(px + nxt), Yn = __ldg(py + nxt), Zn = __ldg(pz + nxt);
         float d[4];
-        if (PERIODIC && wrap) {
-            d[0] = d2_periodic(X.x, Y.x, Z.x, qx, qy, qz, t.box);
-            d[1] = d2_periodic(X.y, Y.y, Z.y, qx, qy, qz, t.box);
-            d[2] = d2_periodic(X.z, Y.z, Z.z, qx, qy, qz, t.box);
-            d[3] = d2_periodic(X.w, Y.w, Z.w, qx, qy, qz, t.box);
-        } else {
-            d[0] = d2_open(X.x, Y.x, Z.x, qx, qy, qz);
-            d[1] = d2_open(X.y, Y.y, Z.y, qx, qy, qz);
-            d[2] = d2_open(X.z, Y.z, Z.z, qx, qy, qz);
-            d[3] = d2_open(X.w, Y.w, Z.w, qx, qy, qz);
-        }
+        leaf_d2x4<WRAP>(X, Y, Z, qx, qy, qz, t.box, d);
+        const float dmin = fminf(fminf(d[0], d[1]), fminf(d[2], d[3]));
+        if (dmin <= top.worst()) {
+            const uint32_t p = begin + 4 * s;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (d[j] <= top.worst()) {
-                unsigned long long cand =
-                    ((unsigned long long)__float_as_uint(d[j]) << 32) | __ldg(t.idx + p + j);
-                if (cand < top.key[K - 1]) top.insert(cand);
+            for (int j = 0; j < 4; ++j) {
+                if (d[j] <= top.worst()) {
+                    unsigned long long cand =
+                        ((unsigned long long)__float_as_uint(d[j]) << 32) | __ldg(t.idx + p + j);
+                    if (cand < top.key[K - 1]) top.insert(cand);
+                }
             }
         }
+        X = Xn; Y = Yn; Z = Zn;
     }
 }
 
@@ -200,9 +215,21 @@ knn_packet_kernel(QueryTree t, const float *__restrict__ q_aos, const uint32_t *
         bool wrap = false;
         float lb;
         if (PERIODIC) {
-            lb = __fadd_rn(__fadd_rn(axis_lb_periodic(e.lo0, e.hi0, qx, t.box, halfL, wrap),
-                                     axis_lb_periodic(e.lo1, e.hi1, qy, t.box, halfL, wrap)),
-                           axis_lb_periodic(e.lo2, e.hi2, qz, t.box, halfL, wrap));
+            // d = fl(p - q) of every point of the cell lies in [a, b] on each axis
+            const float a0 = __fsub_rn(e.lo0, qx), b0 = __fsub_rn(e.hi0, qx);
+            const float a1 = __fsub_rn(e.lo1, qy), b1 = __fsub_rn(e.hi1, qy);
+            const float a2 = __fsub_rn(e.lo2, qz), b2 = __fsub_rn(e.hi2, qz);
+            wrap = fminf(fminf(a0, a1), a2) < -halfL || fmaxf(fmaxf(b0, b1), b2) > halfL;
+            if (__any_sync(0xffffffffu, valid && wrap)) {
+                lb = __fadd_rn(__fadd_rn(axis_lb_periodic(a0, b0, t.box), axis_lb_periodic(a1, b1, t.box)),
+                               axis_lb_periodic(a2, b2, t.box));
+            } else {
+                // |d| <= L/2 on every axis: the periodic term IS d^2 (see axis_periodic), so the
+                // open-form bound max(a, -b, 0)^2 applies
+                const float v0 = fmaxf(fmaxf(a0, -b0), 0.0f), v1 = fmaxf(fmaxf(a1, -b1), 0.0f),
+                            v2 = fmaxf(fmaxf(a2, -b2), 0.0f);
+                lb = __fadd_rn(__fadd_rn(__fmul_rn(v0, v0), __fmul_rn(v1, v1)), __fmul_rn(v2, v2));
+            }
         } else {
             lb = __fadd_rn(__fadd_rn(axis_lb_open(e.lo0, e.hi0, qx), axis_lb_open(e.lo1, e.hi1, qy)),
                            axis_lb_open(e.lo2, e.hi2, qz));
@@ -216,8 +243,10 @@ knn_packet_kernel(QueryTree t, const float *__restrict__ q_aos, const uint32_t *
         if (nd.dim < 0) {
             // lanes that do not need the leaf cannot be hurt by the cheaper open formula: their
             // true d2 >= lb > worst, and the open d2 is never below the periodic one
-            const bool any_wrap = PERIODIC && (__ballot_sync(0xffffffffu, need && wrap) != 0u);
-            scan_leaf<K, PERIODIC>(t, nd.left, nd.right, qx, qy, qz, any_wrap, top);
+            if (PERIODIC && __any_sync(0xffffffffu, need && wrap))
+                scan_leaf<K, true>(t, nd.left, nd.right, qx, qy, qz, top);
+            else
+                scan_leaf<K, false>(t, nd.left, nd.right, qx, qy, qz, top);
             continue;
         }
         const float qd = nd.dim == 0 ? qx : (nd.dim == 1 ? qy : qz);
@@ -235,6 +264,190 @@ knn_packet_kernel(QueryTree t, const float *__restrict__ q_aos, const uint32_t *
         }
         __syncwarp();
         sp += 2;
+    }
+
+    if (valid) {
+        float *od = out_d + (uint64_t)qid * k_out;
+        uint32_t *oi = out_i + (uint64_t)qid * k_out;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            if (j < k_out) {
+                uint32_t bits = (uint32_t)(top.key[j] >> 32);
+                od[j] = __fsqrt_rn(__uint_as_float(bits)); // postprocess, kdtree.cpp:154-156
+                oi[j] = bits == kFltMaxBits ? 0xFFFFFFFFu : (uint32_t)top.key[j];
+            }
+        }
+    }
+}
+
+// ---- the lane kernel: one query per lane, independent traversal -----------------------------------
+//
+// Every lane walks the tree for its own query (closer child first, far children on a per-lane stack
+// in local memory) and scans its own leaves; because consecutive lanes hold Morton-neighbouring
+// queries they mostly visit the same nodes and leaves at the same time, so the loads of a warp
+// collapse to a few broadcast sectors without paying for the union of 32 search regions the way
+// the packet kernel does.
+//
+// Pruning bound.  A cell is described by per-axis terms (t0, t1, t2) whose ordered sum
+// fl(fl(t0 + t1) + t2) never exceeds the d2 of any point inside.  Descending, only the split axis
+// changes: for the far child the term becomes w^2 with w = fl(fl(split - q) + o), the same monotone
+// operations the point distance applies to fl(p - q) (o = 0 for the open metric and for the primary
+// periodic image), so it equals the reference's point-to-box distance (kdtree.hpp:34-45).
+// Periodic metric: min over the three images per axis == min over the 27 image shifts
+// (o0, o1, o2) in {0, +L, -L}^3 of the shifted sum, so the tree is searched once per image whose
+// root bound can still beat the current k-th distance (almost always only the primary one); leaf
+// distances are always the TRUE periodic d2, so a point met again through another image carries
+// the same key and is recognised as a duplicate.
+constexpr int kLaneStack = 32; // one pending far child per level; depth <= log2(2^32 / 16)
+constexpr uint32_t kNoNode = 0xFFFFFFFFu;
+
+__device__ __forceinline__ float root_term(float q, float o, float L) {
+    // points of the periodic root cell have p in [0, L]
+    float a = __fadd_rn(__fsub_rn(0.0f, q), o), b = __fadd_rn(__fsub_rn(L, q), o);
+    float v = fmaxf(fmaxf(a, -b), 0.0f);
+    return __fmul_rn(v, v);
+}
+
+template <int K> __device__ __forceinline__ bool topk_contains(TopK<K> const &top, unsigned long long cand) {
+    bool hit = false;
+#pragma unroll
+    for (int j = 0; j < K; ++j) hit = hit || top.key[j] == cand;
+    return hit;
+}
+
+template <int K, bool PERIODIC>
+__device__ __forceinline__ void scan_leaf_lane(QueryTree const &t, uint32_t begin, uint32_t end, float qx,
+                                               float qy, float qz, float wrap_d2, bool dedupe,
+                                               TopK<K> &top) {
+    const float4 *px = reinterpret_cast<const float4 *>(t.x + begin);
+    const float4 *py = reinterpret_cast<const float4 *>(t.y + begin);
+    const float4 *pz = reinterpret_cast<const float4 *>(t.z + begin);
+    const uint32_t steps = (end - begin) >> 2;
+    for (uint32_t s = 0; s < steps; ++s) {
+        const float4 X = __ldg(px + s), Y = __ldg(py + s), Z = __ldg(pz + s);
+        float d[4];
+        leaf_d2x4<false>(X, Y, Z, qx, qy, qz, t.box, d);
+        if (PERIODIC) {
+            // a wrapped image can only win on an axis with |p - q| > L/2, i.e. open d2 >= (L/2)^2
+            const float dmax = fmaxf(fmaxf(d[0], d[1]), fmaxf(d[2], d[3]));
+            if (dmax >= wrap_d2) leaf_d2x4<true>(X, Y, Z, qx, qy, qz, t.box, d);
+        }
+        const float dmin = fminf(fminf(d[0], d[1]), fminf(d[2], d[3]));
+        if (dmin <= top.worst()) {
+            const uint32_t p = begin + 4 * s;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (d[j] <= top.worst()) {
+                    unsigned long long cand =
+                        ((unsigned long long)__float_as_uint(d[j]) << 32) | __ldg(t.idx + p + j);
+                    if (cand < top.key[K - 1] && !(dedupe && topk_contains(top, cand))) top.insert(cand);
+                }
+            }
+        }
+    }
+}
+
+#ifndef NBK_LANE_MIN_BLOCKS
+#define NBK_LANE_MIN_BLOCKS 8
+#endif
+
+template <int K, bool PERIODIC>
+__global__ void __launch_bounds__(kQueryThreads, NBK_LANE_MIN_BLOCKS)
+knn_lane_kernel(QueryTree t, const float *__restrict__ q_aos, const uint32_t *__restrict__ order,
+                uint64_t m, int k_out, float *__restrict__ out_d, uint32_t *__restrict__ out_i) {
+    const uint64_t slot = (uint64_t)blockIdx.x * kQueryThreads + threadIdx.x;
+    const bool valid = slot < m;
+    if (!__any_sync(0xffffffffu, valid)) return;
+    const uint32_t qid = order[valid ? slot : m - 1];
+    const float qx = q_aos[3 * (uint64_t)qid], qy = q_aos[3 * (uint64_t)qid + 1],
+                qz = q_aos[3 * (uint64_t)qid + 2];
+    const float L = t.box;
+    const float wrap_d2 = __fmul_rn(0.5f * L, 0.5f * L);
+
+    TopK<K> top;
+    top.init();
+
+    float4 stack[kLaneStack]; // (t0, t1, t2, node bits)
+    int sp = 0;
+    int img = 0;                    // 0 = primary image; 1..26 = shifted images (periodic only)
+    float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f;
+    float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f;
+    float min_shift = 0.0f;         // smallest single-axis root term of a shifted image
+    if (PERIODIC) {
+        t0 = root_term(qx, 0.0f, L);
+        t1 = root_term(qy, 0.0f, L);
+        t2 = root_term(qz, 0.0f, L);
+        min_shift = fminf(fminf(fminf(root_term(qx, L, L), root_term(qx, -L, L)),
+                                fminf(root_term(qy, L, L), root_term(qy, -L, L))),
+                          fminf(root_term(qz, L, L), root_term(qz, -L, L)));
+    }
+    uint32_t cur = 0;               // root
+    bool done = !valid;
+    uint32_t lbeg = 0, lend = 0;
+
+    while (true) {
+        // ---- walk until this lane has a leaf to scan (or is finished) -------------------------
+        while (!done && lbeg == lend) {
+            if (cur == kNoNode) {
+                if (sp == 0) {
+                    if (!PERIODIC || !(min_shift <= top.worst())) {
+                        done = true;
+                        break;
+                    }
+                    // rare: the search ball reaches through a face of the box; next image whose
+                    // root bound can still beat the k-th distance
+                    bool found = false;
+                    while (!found && ++img < 27) {
+                        const int s0 = img % 3, s1 = (img / 3) % 3, s2 = img / 9;
+                        o0 = s0 == 0 ? 0.0f : (s0 == 1 ? L : -L);
+                        o1 = s1 == 0 ? 0.0f : (s1 == 1 ? L : -L);
+                        o2 = s2 == 0 ? 0.0f : (s2 == 1 ? L : -L);
+                        t0 = root_term(qx, o0, L);
+                        t1 = root_term(qy, o1, L);
+                        t2 = root_term(qz, o2, L);
+                        found = __fadd_rn(__fadd_rn(t0, t1), t2) <= top.worst();
+                    }
+                    if (!found) {
+                        done = true;
+                        break;
+                    }
+                    cur = 0;
+                    continue;
+                }
+                const float4 e = stack[--sp];
+                if (!(__fadd_rn(__fadd_rn(e.x, e.y), e.z) <= top.worst())) continue;
+                t0 = e.x;
+                t1 = e.y;
+                t2 = e.z;
+                cur = __float_as_uint(e.w);
+            }
+            const int4 raw = __ldg(reinterpret_cast<const int4 *>(t.nodes) + cur);
+            const int dim = raw.x;
+            if (dim < 0) {
+                lbeg = (uint32_t)raw.z;
+                lend = (uint32_t)raw.w;
+                cur = kNoNode;
+                break;
+            }
+            const float split = __int_as_float(raw.y);
+            const float qd = dim == 0 ? qx : (dim == 1 ? qy : qz);
+            float w = __fsub_rn(split, qd);
+            if (PERIODIC) w = __fadd_rn(w, dim == 0 ? o0 : (dim == 1 ? o1 : o2));
+            // w > 0: the (shifted) query lies left of the plane -> left child first
+            const bool left_first = !(w < 0.0f);
+            const uint32_t near = left_first ? (uint32_t)raw.z : (uint32_t)raw.w;
+            const uint32_t far = left_first ? (uint32_t)raw.w : (uint32_t)raw.z;
+            const float ft = __fmul_rn(w, w);
+            const float f0 = dim == 0 ? ft : t0, f1 = dim == 1 ? ft : t1, f2 = dim == 2 ? ft : t2;
+            // non-strict: an equal-distance point with a smaller index must still be found
+            if (__fadd_rn(__fadd_rn(f0, f1), f2) <= top.worst())
+                stack[sp++] = make_float4(f0, f1, f2, __uint_as_float(far));
+            cur = near;
+        }
+        if (!__any_sync(0xffffffffu, lbeg != lend)) break;
+        // ---- scan it ------------------------------------------------------------------------------
+        scan_leaf_lane<K, PERIODIC>(t, lbeg, lend, qx, qy, qz, wrap_d2, PERIODIC && img > 0, top);
+        lbeg = lend = 0;
     }
 
     if (valid) {

@@ -1,6 +1,7 @@
 // libnbk.so -- C ABI (include/nbk.h) over the sm_100a build and query kernels.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -235,11 +236,23 @@ struct SectionTimer {
 };
 
 // ---- query -----------------------------------------------------------------------------------------
+// NBK_KERNEL=packet selects the warp-packet traversal kernel; default is the per-lane kernel.
+inline bool use_packet_kernel() {
+    static const bool packet = [] {
+        const char *v = std::getenv("NBK_KERNEL");
+        return v && std::string(v) == "packet";
+    }();
+    return packet;
+}
+
 template <int K, bool P>
 void launch_packet(QueryTree const &qt, const float *d_q, const uint32_t *order, uint64_t m, int k,
                    float *d_out_d, uint32_t *d_out_i, cudaStream_t stream) {
     unsigned grid = (unsigned)div_up(m, kQueryThreads);
-    knn_packet_kernel<K, P><<<grid, kQueryThreads, 0, stream>>>(qt, d_q, order, m, k, d_out_d, d_out_i);
+    if (use_packet_kernel())
+        knn_packet_kernel<K, P><<<grid, kQueryThreads, 0, stream>>>(qt, d_q, order, m, k, d_out_d, d_out_i);
+    else
+        knn_lane_kernel<K, P><<<grid, kQueryThreads, 0, stream>>>(qt, d_q, order, m, k, d_out_d, d_out_i);
     NBK_LAUNCHED();
 }
 
