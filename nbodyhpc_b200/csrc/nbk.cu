@@ -474,31 +474,39 @@ int nbk_tree_query_ex(const nbk_tree *tree, const float *q_aos, uint64_t m, int 
         if (k > kMaxK) throw Error(NBK_ERR_INVALID, "k > 64 is not supported by this build");
         if (m == 0) return;
         DeviceGuard guard(tree->device);
-        // Two chunks in flight: chunk c+1 uploads/computes while chunk c downloads.
-        const uint64_t chunk = std::min<uint64_t>(m, 1ull << 22);
-        cudaStream_t streams[2];
-        float *d_q[2] = {nullptr, nullptr}, *d_d[2] = {nullptr, nullptr};
-        uint32_t *d_i[2] = {nullptr, nullptr};
-        for (int s = 0; s < 2; ++s) NBK_CUDA(cudaStreamCreateWithFlags(&streams[s], cudaStreamNonBlocking));
+        // Up to three slices in flight, one stream each: slice c+2 uploads while slice c+1 computes
+        // and slice c downloads.  A slice is ordered (Morton sort) on its own, so it has to be large
+        // enough that neighbouring queries of a warp still share leaves: 2^24 queries by default.
+        static const uint64_t slice_cfg = [] {
+            const char *v = std::getenv("NBK_HOST_SLICE");
+            uint64_t n = v ? std::strtoull(v, nullptr, 10) : 0;
+            return n ? n : (1ull << 24);
+        }();
+        const uint64_t slice = std::min<uint64_t>(m, slice_cfg);
+        const int nbuf = (int)std::min<uint64_t>(3, div_up(m, slice));
+        cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+        float *d_q[3] = {}, *d_d[3] = {};
+        uint32_t *d_i[3] = {};
         auto cleanup = [&] {
-            for (int s = 0; s < 2; ++s) {
+            for (int s = 0; s < nbuf; ++s) {
+                if (!streams[s]) continue;
+                if (d_q[s]) cudaFreeAsync(d_q[s], streams[s]);
+                if (d_d[s]) cudaFreeAsync(d_d[s], streams[s]);
+                if (d_i[s]) cudaFreeAsync(d_i[s], streams[s]);
                 cudaStreamSynchronize(streams[s]);
-                cudaFree(d_q[s]);
-                cudaFree(d_d[s]);
-                cudaFree(d_i[s]);
                 cudaStreamDestroy(streams[s]);
             }
         };
         try {
-            int nbuf = m > chunk ? 2 : 1;
             for (int s = 0; s < nbuf; ++s) {
-                NBK_CUDA(cudaMalloc(&d_q[s], chunk * 12));
-                NBK_CUDA(cudaMalloc(&d_d[s], chunk * (uint64_t)k * 4));
-                NBK_CUDA(cudaMalloc(&d_i[s], chunk * (uint64_t)k * 4));
+                NBK_CUDA(cudaStreamCreateWithFlags(&streams[s], cudaStreamNonBlocking));
+                NBK_CUDA(cudaMallocAsync(&d_q[s], slice * 12, streams[s]));
+                NBK_CUDA(cudaMallocAsync(&d_d[s], slice * (uint64_t)k * 4, streams[s]));
+                NBK_CUDA(cudaMallocAsync(&d_i[s], slice * (uint64_t)k * 4, streams[s]));
             }
             int s = 0;
-            for (uint64_t begin = 0; begin < m; begin += chunk, s ^= (nbuf - 1)) {
-                uint64_t cnt = std::min(chunk, m - begin);
+            for (uint64_t begin = 0; begin < m; begin += slice, s = (s + 1) % nbuf) {
+                uint64_t cnt = std::min(slice, m - begin);
                 cudaStream_t st = streams[s];
                 NBK_CUDA(cudaMemcpyAsync(d_q[s], q_aos + begin * 3, cnt * 12, cudaMemcpyHostToDevice, st));
                 query_device(*tree, d_q[s], cnt, k, d_d[s], d_i[s], st, periodic, box_size);
@@ -507,7 +515,7 @@ int nbk_tree_query_ex(const nbk_tree *tree, const float *q_aos, uint64_t m, int 
                 NBK_CUDA(cudaMemcpyAsync(out_idx + begin * k, d_i[s], cnt * (uint64_t)k * 4,
                                          cudaMemcpyDeviceToHost, st));
             }
-            for (int t = 0; t < 2; ++t) NBK_CUDA(cudaStreamSynchronize(streams[t]));
+            for (int t = 0; t < nbuf; ++t) NBK_CUDA(cudaStreamSynchronize(streams[t]));
         } catch (...) {
             cleanup();
             throw;
