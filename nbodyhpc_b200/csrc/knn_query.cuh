@@ -3,15 +3,18 @@
 // Replaces PyKDTree::query -> KDTree::find_closest -> KDTreeQuery::compute -> asm leaf scan
 // (pybind.cpp:90-189, kdtree.cpp:133-159, kdtree_impl.hpp:212-268, kdtree_asm_systemv.asm:121-248).
 //
-// Design: queries are ordered along a Morton curve, so 32 consecutive queries are
-// spatial neighbours.  One warp walks the tree ONCE for its 32 queries (one query per lane): the
-// node stack is warp-uniform and lives in shared memory, a subtree is entered when ANY lane's
-// exact lower bound to its cell does not exceed that lane's current k-th distance, and every leaf
-// point is fetched once per warp with warp-uniform 16-byte loads and evaluated by all 32 lanes.
-// The top-k of each lane is a register-resident sorted list of 64-bit (d2 bits, index) keys, so the
-// result is the exact top-k under the total order (d2, index) no matter in which order nodes are
-// visited -- which is what makes the answer independent of the traversal and equal to the
-// reference's (whose own result is traversal dependent only for exact d2 ties).
+// Queries are ordered along a Morton curve, so the 32 lanes of a warp hold spatial neighbours.
+//
+//   knn_lane_kernel   (default) one query per lane, every lane walks the tree on its own; neighbouring
+//                     lanes mostly visit the same nodes and leaf tiles at the same time, so a warp's
+//                     loads collapse to a few broadcast sectors.
+//   knn_packet_kernel (NBK_KERNEL=packet) one warp walks the tree once for its 32 queries with a
+//                     warp-uniform stack; kept as the measured alternative.
+//
+// The top-k of a lane is a register-resident sorted list of 64-bit keys (d2 bits << 32 | index),
+// so the result is the exact top-k under the total order (d2, index) whatever the visiting order --
+// which is what makes the answer independent of the traversal and equal to the reference's (whose
+// own result is traversal dependent only for exact d2 ties).
 //
 // Arithmetic contract: d2 is computed with __fsub_rn/__fmul_rn/__fadd_rn (never contracted into
 // FMA) in the reference's order ((dx2 + dy2) + dz2) with d = p - q (kdtree_asm_systemv.asm:76-87),
@@ -22,25 +25,26 @@
 
 namespace nbk {
 
+// Leaf-ordered points live in 128-byte tiles of 8 points: {x[8], y[8], z[8], idx[8]}.  Leaves start
+// on multiples of 8 points and hold a multiple of 8 (block_size 8, kdtree_impl.hpp:108-110), so a
+// leaf is a run of whole tiles and one tile is exactly one cache line.
+constexpr int kTilePoints = 8;
+constexpr int kTileFloat4 = 8; // float4 per tile: x0 x1 y0 y1 z0 z1 i0 i1
+
 struct QueryTree {
     const nbk_node *nodes;
-    const float *x, *y, *z;
-    const uint32_t *idx;
+    const float4 *tiles;
     bool periodic;
-    float box;      // periodic box size
+    float box;          // periodic box size
     float lo[3], hi[3]; // root cell: periodic [0, box]; open [-FLT_MAX, FLT_MAX]
 };
 
+__device__ __forceinline__ float tile_coord(const float4 *tiles, uint32_t p, int axis) {
+    return reinterpret_cast<const float *>(tiles)[(uint64_t)(p >> 3) * 32 + axis * 8 + (p & 7)];
+}
+
 constexpr int kQueryThreads = 128;
 constexpr int kQueryWarps = kQueryThreads / 32;
-constexpr int kMaxStack = 48; // pushes two, pops one per internal node: depth + 1 entries
-
-struct __align__(16) StackEntry {
-    float lo0, lo1, lo2;
-    uint32_t node;
-    float hi0, hi1, hi2;
-    uint32_t pad;
-};
 
 // ---- Morton ordering of the queries --------------------------------------------------------------
 __device__ __forceinline__ uint32_t spread10(uint32_t v) {
@@ -66,31 +70,6 @@ morton_keys_kernel(const float *__restrict__ q_aos, uint64_t m, float lo0, float
     vals[i] = (uint32_t)i;
 }
 
-// ---- exact lower bounds from a query to an axis-aligned cell ------------------------------------
-// Both bounds never exceed the d2 this file computes for any point inside the cell, because every
-// step is the same monotone float operation applied to the end points of the interval the point's
-// coordinate lies in ("pruning is exact").
-
-// open metric: identical to L2Distance::box_distance (kdtree.hpp:34-45)
-__device__ __forceinline__ float axis_lb_open(float lo, float hi, float q) {
-    float dl = fmaxf(__fsub_rn(lo, q), 0.0f);
-    float dr = fmaxf(__fsub_rn(q, hi), 0.0f);
-    return __fadd_rn(__fmul_rn(dl, dl), __fmul_rn(dr, dr));
-}
-
-// periodic metric: lower bound of min(d^2, (d+L)^2, (d-L)^2) over d = fl(p - q) in [a, b]
-// (a = fl(lo - q), b = fl(hi - q)): each image interval is the same monotone operation applied to
-// the end points, and the distance of an interval [u, v] from zero is max(u, -v, 0).
-__device__ __forceinline__ float axis_lb_periodic(float a, float b, float L) {
-    float v0 = fmaxf(fmaxf(a, -b), 0.0f);
-    float ap = __fadd_rn(a, L), bp = __fadd_rn(b, L);
-    float vp = fmaxf(fmaxf(ap, -bp), 0.0f);
-    float am = __fsub_rn(a, L), bm = __fsub_rn(b, L);
-    float vm = fmaxf(fmaxf(am, -bm), 0.0f);
-    float v = fminf(v0, fminf(vp, vm));
-    return __fmul_rn(v, v);
-}
-
 // ---- point distance -------------------------------------------------------------------------------
 __device__ __forceinline__ float d2_open(float px, float py, float pz, float qx, float qy,
                                          float qz) {
@@ -112,36 +91,9 @@ __device__ __forceinline__ float d2_periodic(float px, float py, float pz, float
                      axis_periodic(pz, qz, L));
 }
 
-// ---- register-resident top-k ----------------------------------------------------------------------
-// keys sorted ascending; key = (d2 bits << 32) | index.  d2 >= +0 so the bit pattern orders like the
-// float.  Empty slots hold (FLT_MAX, 0): a candidate at d2 == FLT_MAX never replaces one
-// (the reference inserts only if d2 < FLT_MAX, kdtree_impl.hpp:210 + strict <).
-template <int K> struct TopK {
-    unsigned long long key[K];
-    __device__ __forceinline__ void init() {
-#pragma unroll
-        for (int j = 0; j < K; ++j) key[j] = (unsigned long long)kFltMaxBits << 32;
-    }
-    __device__ __forceinline__ float worst() const {
-        return __uint_as_float((uint32_t)(key[K - 1] >> 32));
-    }
-    __device__ __forceinline__ void insert(unsigned long long cand) {
-        // precondition: cand < key[K-1]
-        key[K - 1] = cand;
-#pragma unroll
-        for (int j = K - 1; j > 0; --j) {
-            unsigned long long a = key[j - 1], b = key[j];
-            bool sw = b < a;
-            key[j - 1] = sw ? b : a;
-            key[j] = sw ? a : b;
-        }
-    }
-};
-
-// ---- the packet kernel ------------------------------------------------------------------------------
 template <bool WRAP>
-__device__ __forceinline__ void leaf_d2x4(float4 const &X, float4 const &Y, float4 const &Z, float qx,
-                                          float qy, float qz, float L, float d[4]) {
+__device__ __forceinline__ void d2x4(float4 const &X, float4 const &Y, float4 const &Z, float qx,
+                                     float qy, float qz, float L, float d[4]) {
     if (WRAP) {
         d[0] = d2_periodic(X.x, Y.x, Z.x, qx, qy, qz, L);
         d[1] = d2_periodic(X.y, Y.y, Z.y, qx, qy, qz, L);
@@ -155,138 +107,95 @@ __device__ __forceinline__ void leaf_d2x4(float4 const &X, float4 const &Y, floa
     }
 }
 
-// One leaf for all 32 lanes.  Leaves start on multiples of 8 points and hold a multiple of 8
-// (block_size 8), so every step is three warp-uniform 16-byte loads (x, y, z of 4 points); the
-// loads of step i+1 are issued before the arithmetic of step i.
-template <int K, bool WRAP>
-__device__ __forceinline__ void scan_leaf(QueryTree const &t, uint32_t begin, uint32_t end, float qx,
-                                          float qy, float qz, TopK<K> &top) {
-    const float4 *px = reinterpret_cast<const float4 *>(t.x + begin);
-    const float4 *py = reinterpret_cast<const float4 *>(t.y + begin);
-    const float4 *pz = reinterpret_cast<const float4 *>(t.z + begin);
-    const uint32_t steps = (end - begin) >> 2;
-    float4 X = __ldg(px), Y = __ldg(py), Z = __ldg(pz);
-    for (uint32_t s = 0; s < steps; ++s) {
-        const uint32_t nxt = s + 1 < steps ? s + 1 : s;
-        const float4 Xn = __ldg(px + nxt), Yn = __ldg(py + nxt), Zn = __ldg(pz + nxt);
-        float d[4];
-        leaf_d2x4<WRAP>(X, Y, Z, qx, qy, qz, t.box, d);
-        const float dmin = fminf(fminf(d[0], d[1]), fminf(d[2], d[3]));
-        if (dmin <= top.worst()) {
-            const uint32_t p = begin + 4 * s;
+// ---- register-resident top-k ----------------------------------------------------------------------
+// keys sorted ascending; key = (d2 bits << 32) | index, held as two 32-bit halves.  d2 >= +0 so the
+// bit pattern orders like the float.  Empty slots hold (FLT_MAX, 0): a candidate at d2 == FLT_MAX
+// never replaces one (the reference inserts only if d2 < FLT_MAX, kdtree_impl.hpp:210 + strict <).
+template <int K> struct TopK {
+    uint32_t hi[K], lo[K];
+    __device__ __forceinline__ void init() {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (d[j] <= top.worst()) {
-                    unsigned long long cand =
-                        ((unsigned long long)__float_as_uint(d[j]) << 32) | __ldg(t.idx + p + j);
-                    if (cand < top.key[K - 1]) top.insert(cand);
-                }
-            }
+        for (int j = 0; j < K; ++j) {
+            hi[j] = kFltMaxBits;
+            lo[j] = 0u;
         }
-        X = Xn; Y = Yn; Z = Zn;
+    }
+    __device__ __forceinline__ float worst() const { return __uint_as_float(hi[K - 1]); }
+    __device__ __forceinline__ bool beats_worst(uint32_t chi, uint32_t clo) const {
+        return chi < hi[K - 1] || (chi == hi[K - 1] && clo < lo[K - 1]);
+    }
+    __device__ __forceinline__ bool contains(uint32_t chi, uint32_t clo) const {
+        bool hit = false;
+#pragma unroll
+        for (int j = 0; j < K; ++j) hit = hit || (hi[j] == chi && lo[j] == clo);
+        return hit;
+    }
+    // precondition: beats_worst(chi, clo).  One 64-bit compare (2 instructions) + 4 selects per step.
+    __device__ __forceinline__ void insert(uint32_t chi, uint32_t clo) {
+        hi[K - 1] = chi;
+        lo[K - 1] = clo;
+#pragma unroll
+        for (int j = K - 1; j > 0; --j) {
+            uint32_t ah = hi[j - 1], al = lo[j - 1], bh = hi[j], bl = lo[j];
+            asm("{\n\t.reg .pred p;\n\t.reg .b64 ka, kb;\n\t"
+                "mov.b64 ka, {%4, %5};\n\tmov.b64 kb, {%6, %7};\n\t"
+                "setp.lt.u64 p, kb, ka;\n\t"
+                "selp.b32 %0, %6, %4, p;\n\tselp.b32 %1, %7, %5, p;\n\t"
+                "selp.b32 %2, %4, %6, p;\n\tselp.b32 %3, %5, %7, p;\n\t}"
+                : "=&r"(lo[j - 1]), "=&r"(hi[j - 1]), "=&r"(lo[j]), "=&r"(hi[j])
+                : "r"(al), "r"(ah), "r"(bl), "r"(bh));
+        }
+    }
+};
+
+template <int K>
+__device__ __forceinline__ void write_row(TopK<K> const &top, uint32_t qid, int k_out,
+                                          float *__restrict__ out_d, uint32_t *__restrict__ out_i) {
+    float *od = out_d + (uint64_t)qid * k_out;
+    uint32_t *oi = out_i + (uint64_t)qid * k_out;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        if (j < k_out) {
+            od[j] = __fsqrt_rn(__uint_as_float(top.hi[j])); // postprocess, kdtree.cpp:154-156
+            oi[j] = top.hi[j] == kFltMaxBits ? 0xFFFFFFFFu : top.lo[j];
+        }
     }
 }
 
+// Scans the tiles [begin, end) of one leaf for this lane's query.  Per 4 points: x, y, z and the
+// indices are four 16-byte loads from one 128-byte tile.  PERIODIC: a wrapped image can only win on
+// an axis with |p - q| > L/2, i.e. when the open d2 is >= (L/2)^2 = wrap_d2; only then is the
+// 3-image formula evaluated.  `dedupe` is set while a shifted image is searched.
 template <int K, bool PERIODIC>
-__global__ void __launch_bounds__(kQueryThreads)
-knn_packet_kernel(QueryTree t, const float *__restrict__ q_aos, const uint32_t *__restrict__ order,
-                  uint64_t m, int k_out, float *__restrict__ out_d, uint32_t *__restrict__ out_i) {
-    __shared__ StackEntry stack[kQueryWarps][kMaxStack];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint64_t slot = (uint64_t)blockIdx.x * kQueryThreads + threadIdx.x;
-    const bool valid = slot < m;
-    if (!__any_sync(0xffffffffu, valid)) return;
-    const uint32_t qid = order[valid ? slot : m - 1];
-    const float qx = q_aos[3 * (uint64_t)qid], qy = q_aos[3 * (uint64_t)qid + 1],
-                qz = q_aos[3 * (uint64_t)qid + 2];
-    const float halfL = 0.5f * t.box;
-
-    TopK<K> top;
-    top.init();
-
-    StackEntry *st = stack[warp];
-    if (lane == 0) st[0] = StackEntry{t.lo[0], t.lo[1], t.lo[2], 0u, t.hi[0], t.hi[1], t.hi[2], 0u};
-    __syncwarp();
-    int sp = 1;
-    while (sp > 0) {
-        --sp;
-        const StackEntry e = st[sp];
-        __syncwarp(); // everyone has read the entry before lane 0 overwrites the slot
-        bool wrap = false;
-        float lb;
+__device__ __forceinline__ void scan_leaf(QueryTree const &t, uint32_t begin, uint32_t end, float qx,
+                                          float qy, float qz, float wrap_d2, bool dedupe,
+                                          TopK<K> &top) {
+    const float4 *tp = t.tiles + (uint64_t)(begin >> 3) * kTileFloat4;
+    const uint32_t steps = (end - begin) >> 2;
+    for (uint32_t s = 0; s < steps; ++s) {
+        const float4 *g = tp + ((s >> 1) << 3) + (s & 1);
+        const float4 X = __ldg(g), Y = __ldg(g + 2), Z = __ldg(g + 4);
+        const uint4 I = __ldg(reinterpret_cast<const uint4 *>(g + 6));
+        float d[4];
+        d2x4<false>(X, Y, Z, qx, qy, qz, t.box, d);
         if (PERIODIC) {
-            // d = fl(p - q) of every point of the cell lies in [a, b] on each axis
-            const float a0 = __fsub_rn(e.lo0, qx), b0 = __fsub_rn(e.hi0, qx);
-            const float a1 = __fsub_rn(e.lo1, qy), b1 = __fsub_rn(e.hi1, qy);
-            const float a2 = __fsub_rn(e.lo2, qz), b2 = __fsub_rn(e.hi2, qz);
-            wrap = fminf(fminf(a0, a1), a2) < -halfL || fmaxf(fmaxf(b0, b1), b2) > halfL;
-            if (__any_sync(0xffffffffu, valid && wrap)) {
-                lb = __fadd_rn(__fadd_rn(axis_lb_periodic(a0, b0, t.box), axis_lb_periodic(a1, b1, t.box)),
-                               axis_lb_periodic(a2, b2, t.box));
-            } else {
-                // |d| <= L/2 on every axis: the periodic term IS d^2 (see axis_periodic), so the
-                // open-form bound max(a, -b, 0)^2 applies
-                const float v0 = fmaxf(fmaxf(a0, -b0), 0.0f), v1 = fmaxf(fmaxf(a1, -b1), 0.0f),
-                            v2 = fmaxf(fmaxf(a2, -b2), 0.0f);
-                lb = __fadd_rn(__fadd_rn(__fmul_rn(v0, v0), __fmul_rn(v1, v1)), __fmul_rn(v2, v2));
-            }
-        } else {
-            lb = __fadd_rn(__fadd_rn(axis_lb_open(e.lo0, e.hi0, qx), axis_lb_open(e.lo1, e.hi1, qy)),
-                           axis_lb_open(e.lo2, e.hi2, qz));
+            const float dmax = fmaxf(fmaxf(d[0], d[1]), fmaxf(d[2], d[3]));
+            if (dmax >= wrap_d2) d2x4<true>(X, Y, Z, qx, qy, qz, t.box, d);
         }
-        // non-strict: an equal-distance point with a smaller index must still be found
-        const bool need = valid && lb <= top.worst();
-        const unsigned need_mask = __ballot_sync(0xffffffffu, need);
-        if (need_mask == 0u) continue;
-        const nbk_node nd = *reinterpret_cast<const nbk_node *>(
-            &reinterpret_cast<const int4 *>(t.nodes)[e.node]);
-        if (nd.dim < 0) {
-            // lanes that do not need the leaf cannot be hurt by the cheaper open formula: their
-            // true d2 >= lb > worst, and the open d2 is never below the periodic one
-            if (PERIODIC && __any_sync(0xffffffffu, need && wrap))
-                scan_leaf<K, true>(t, nd.left, nd.right, qx, qy, qz, top);
-            else
-                scan_leaf<K, false>(t, nd.left, nd.right, qx, qy, qz, top);
-            continue;
-        }
-        const float qd = nd.dim == 0 ? qx : (nd.dim == 1 ? qy : qz);
-        const unsigned right_mask = __ballot_sync(0xffffffffu, need && qd > nd.split);
-        const bool right_first = 2 * __popc(right_mask) > __popc(need_mask);
-        if (lane == 0) {
-            StackEntry l = e, r = e;
-            l.node = nd.left;
-            r.node = nd.right;
-            if (nd.dim == 0) { l.hi0 = nd.split; r.lo0 = nd.split; }
-            else if (nd.dim == 1) { l.hi1 = nd.split; r.lo1 = nd.split; }
-            else { l.hi2 = nd.split; r.lo2 = nd.split; }
-            st[sp] = right_first ? l : r;     // visited second
-            st[sp + 1] = right_first ? r : l; // visited first
-        }
-        __syncwarp();
-        sp += 2;
-    }
-
-    if (valid) {
-        float *od = out_d + (uint64_t)qid * k_out;
-        uint32_t *oi = out_i + (uint64_t)qid * k_out;
+        const float dmin = fminf(fminf(d[0], d[1]), fminf(d[2], d[3]));
+        if (dmin <= top.worst()) {
+            const uint32_t idx[4] = {I.x, I.y, I.z, I.w};
 #pragma unroll
-        for (int j = 0; j < K; ++j) {
-            if (j < k_out) {
-                uint32_t bits = (uint32_t)(top.key[j] >> 32);
-                od[j] = __fsqrt_rn(__uint_as_float(bits)); // postprocess, kdtree.cpp:154-156
-                oi[j] = bits == kFltMaxBits ? 0xFFFFFFFFu : (uint32_t)top.key[j];
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t chi = __float_as_uint(d[j]);
+                if (top.beats_worst(chi, idx[j]) && !(dedupe && top.contains(chi, idx[j])))
+                    top.insert(chi, idx[j]);
             }
         }
     }
 }
 
 // ---- the lane kernel: one query per lane, independent traversal -----------------------------------
-//
-// Every lane walks the tree for its own query (closer child first, far children on a per-lane stack
-// in local memory) and scans its own leaves; because consecutive lanes hold Morton-neighbouring
-// queries they mostly visit the same nodes and leaves at the same time, so the loads of a warp
-// collapse to a few broadcast sectors without paying for the union of 32 search regions the way
-// the packet kernel does.
 //
 // Pruning bound.  A cell is described by per-axis terms (t0, t1, t2) whose ordered sum
 // fl(fl(t0 + t1) + t2) never exceeds the d2 of any point inside.  Descending, only the split axis
@@ -295,9 +204,12 @@ knn_packet_kernel(QueryTree t, const float *__restrict__ q_aos, const uint32_t *
 // periodic image), so it equals the reference's point-to-box distance (kdtree.hpp:34-45).
 // Periodic metric: min over the three images per axis == min over the 27 image shifts
 // (o0, o1, o2) in {0, +L, -L}^3 of the shifted sum, so the tree is searched once per image whose
-// root bound can still beat the current k-th distance (almost always only the primary one); leaf
-// distances are always the TRUE periodic d2, so a point met again through another image carries
-// the same key and is recognised as a duplicate.
+// root bound can still beat the current k-th distance.  Almost always that is only the primary
+// image: the fast instantiation (IMAGES = false) searches just that one and, if a shifted image could
+// still matter (the search ball reaches through a face of the box), defers the query to a work list
+// that the general instantiation (IMAGES = true) answers from scratch.  Leaf distances are always
+// the TRUE periodic d2, so a point met again through another image carries the same key and is
+// recognised as a duplicate.
 constexpr int kLaneStack = 32; // one pending far child per level; depth <= log2(2^32 / 16)
 constexpr uint32_t kNoNode = 0xFFFFFFFFu;
 
@@ -308,56 +220,41 @@ __device__ __forceinline__ float root_term(float q, float o, float L) {
     return __fmul_rn(v, v);
 }
 
-template <int K> __device__ __forceinline__ bool topk_contains(TopK<K> const &top, unsigned long long cand) {
-    bool hit = false;
-#pragma unroll
-    for (int j = 0; j < K; ++j) hit = hit || top.key[j] == cand;
-    return hit;
-}
-
-template <int K, bool PERIODIC>
-__device__ __forceinline__ void scan_leaf_lane(QueryTree const &t, uint32_t begin, uint32_t end, float qx,
-                                               float qy, float qz, float wrap_d2, bool dedupe,
-                                               TopK<K> &top) {
-    const float4 *px = reinterpret_cast<const float4 *>(t.x + begin);
-    const float4 *py = reinterpret_cast<const float4 *>(t.y + begin);
-    const float4 *pz = reinterpret_cast<const float4 *>(t.z + begin);
-    const uint32_t steps = (end - begin) >> 2;
-    for (uint32_t s = 0; s < steps; ++s) {
-        const float4 X = __ldg(px + s), Y = __ldg(py + s), Z = __ldg(pz + s);
-        float d[4];
-        leaf_d2x4<false>(X, Y, Z, qx, qy, qz, t.box, d);
-        if (PERIODIC) {
-            // a wrapped image can only win on an axis with |p - q| > L/2, i.e. open d2 >= (L/2)^2
-            const float dmax = fmaxf(fmaxf(d[0], d[1]), fmaxf(d[2], d[3]));
-            if (dmax >= wrap_d2) leaf_d2x4<true>(X, Y, Z, qx, qy, qz, t.box, d);
-        }
-        const float dmin = fminf(fminf(d[0], d[1]), fminf(d[2], d[3]));
-        if (dmin <= top.worst()) {
-            const uint32_t p = begin + 4 * s;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (d[j] <= top.worst()) {
-                    unsigned long long cand =
-                        ((unsigned long long)__float_as_uint(d[j]) << 32) | __ldg(t.idx + p + j);
-                    if (cand < top.key[K - 1] && !(dedupe && topk_contains(top, cand))) top.insert(cand);
-                }
-            }
-        }
-    }
+// smallest root bound of any shifted image = smallest single-axis shifted term (the other axes
+// contribute >= 0)
+__device__ __forceinline__ float min_shifted_root_term(float qx, float qy, float qz, float L) {
+    return fminf(fminf(fminf(root_term(qx, L, L), root_term(qx, -L, L)),
+                       fminf(root_term(qy, L, L), root_term(qy, -L, L))),
+                 fminf(root_term(qz, L, L), root_term(qz, -L, L)));
 }
 
 #ifndef NBK_LANE_MIN_BLOCKS
 #define NBK_LANE_MIN_BLOCKS 8
 #endif
 
-template <int K, bool PERIODIC>
-__global__ void __launch_bounds__(kQueryThreads, NBK_LANE_MIN_BLOCKS)
+struct DeferList {
+    uint32_t *slots; // sorted-order slots of deferred queries
+    uint32_t *count;
+};
+
+template <int K, bool PERIODIC, bool IMAGES>
+__global__ void __launch_bounds__(kQueryThreads, IMAGES ? 1 : NBK_LANE_MIN_BLOCKS)
 knn_lane_kernel(QueryTree t, const float *__restrict__ q_aos, const uint32_t *__restrict__ order,
-                uint64_t m, int k_out, float *__restrict__ out_d, uint32_t *__restrict__ out_i) {
-    const uint64_t slot = (uint64_t)blockIdx.x * kQueryThreads + threadIdx.x;
-    const bool valid = slot < m;
-    if (!__any_sync(0xffffffffu, valid)) return;
+                uint64_t m, int k_out, float *__restrict__ out_d, uint32_t *__restrict__ out_i,
+                DeferList defer) {
+    static_assert(PERIODIC || !IMAGES, "image shifts exist only for the periodic metric");
+    uint64_t slot = (uint64_t)blockIdx.x * kQueryThreads + threadIdx.x;
+    bool valid;
+    if (IMAGES) {
+        // second pass: the deferred queries, one per thread of a grid sized for the worst case
+        const uint32_t n = *defer.count;
+        valid = slot < n;
+        if (!__any_sync(0xffffffffu, valid)) return;
+        slot = defer.slots[valid ? slot : 0];
+    } else {
+        valid = slot < m;
+        if (!__any_sync(0xffffffffu, valid)) return;
+    }
     const uint32_t qid = order[valid ? slot : m - 1];
     const float qx = q_aos[3 * (uint64_t)qid], qy = q_aos[3 * (uint64_t)qid + 1],
                 qz = q_aos[3 * (uint64_t)qid + 2];
@@ -369,19 +266,15 @@ knn_lane_kernel(QueryTree t, const float *__restrict__ q_aos, const uint32_t *__
 
     float4 stack[kLaneStack]; // (t0, t1, t2, node bits)
     int sp = 0;
-    int img = 0;                    // 0 = primary image; 1..26 = shifted images (periodic only)
+    int img = 0; // 0 = primary image; 1..26 = shifted images (IMAGES only)
     float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f;
     float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f;
-    float min_shift = 0.0f;         // smallest single-axis root term of a shifted image
     if (PERIODIC) {
         t0 = root_term(qx, 0.0f, L);
         t1 = root_term(qy, 0.0f, L);
         t2 = root_term(qz, 0.0f, L);
-        min_shift = fminf(fminf(fminf(root_term(qx, L, L), root_term(qx, -L, L)),
-                                fminf(root_term(qy, L, L), root_term(qy, -L, L))),
-                          fminf(root_term(qz, L, L), root_term(qz, -L, L)));
     }
-    uint32_t cur = 0;               // root
+    uint32_t cur = 0; // root
     bool done = !valid;
     uint32_t lbeg = 0, lend = 0;
 
@@ -390,12 +283,11 @@ knn_lane_kernel(QueryTree t, const float *__restrict__ q_aos, const uint32_t *__
         while (!done && lbeg == lend) {
             if (cur == kNoNode) {
                 if (sp == 0) {
-                    if (!PERIODIC || !(min_shift <= top.worst())) {
+                    if (!IMAGES) {
                         done = true;
                         break;
                     }
-                    // rare: the search ball reaches through a face of the box; next image whose
-                    // root bound can still beat the k-th distance
+                    // next image whose root bound can still beat the k-th distance
                     bool found = false;
                     while (!found && ++img < 27) {
                         const int s0 = img % 3, s1 = (img / 3) % 3, s2 = img / 9;
@@ -432,7 +324,7 @@ knn_lane_kernel(QueryTree t, const float *__restrict__ q_aos, const uint32_t *__
             const float split = __int_as_float(raw.y);
             const float qd = dim == 0 ? qx : (dim == 1 ? qy : qz);
             float w = __fsub_rn(split, qd);
-            if (PERIODIC) w = __fadd_rn(w, dim == 0 ? o0 : (dim == 1 ? o1 : o2));
+            if (IMAGES) w = __fadd_rn(w, dim == 0 ? o0 : (dim == 1 ? o1 : o2));
             // w > 0: the (shifted) query lies left of the plane -> left child first
             const bool left_first = !(w < 0.0f);
             const uint32_t near = left_first ? (uint32_t)raw.z : (uint32_t)raw.w;
@@ -446,22 +338,112 @@ knn_lane_kernel(QueryTree t, const float *__restrict__ q_aos, const uint32_t *__
         }
         if (!__any_sync(0xffffffffu, lbeg != lend)) break;
         // ---- scan it ------------------------------------------------------------------------------
-        scan_leaf_lane<K, PERIODIC>(t, lbeg, lend, qx, qy, qz, wrap_d2, PERIODIC && img > 0, top);
+        scan_leaf<K, PERIODIC>(t, lbeg, lend, qx, qy, qz, wrap_d2, IMAGES && img > 0, top);
         lbeg = lend = 0;
     }
 
-    if (valid) {
-        float *od = out_d + (uint64_t)qid * k_out;
-        uint32_t *oi = out_i + (uint64_t)qid * k_out;
-#pragma unroll
-        for (int j = 0; j < K; ++j) {
-            if (j < k_out) {
-                uint32_t bits = (uint32_t)(top.key[j] >> 32);
-                od[j] = __fsqrt_rn(__uint_as_float(bits)); // postprocess, kdtree.cpp:154-156
-                oi[j] = bits == kFltMaxBits ? 0xFFFFFFFFu : (uint32_t)top.key[j];
-            }
+    if (!valid) return;
+    if (PERIODIC && !IMAGES) {
+        if (min_shifted_root_term(qx, qy, qz, L) <= top.worst()) {
+            defer.slots[atomicAdd(defer.count, 1u)] = (uint32_t)slot;
+            return;
         }
     }
+    write_row<K>(top, qid, k_out, out_d, out_i);
+}
+
+// ---- the packet kernel -----------------------------------------------------------------------------
+constexpr int kMaxStack = 48; // pushes two, pops one per internal node: depth + 1 entries
+
+struct __align__(16) StackEntry {
+    float lo0, lo1, lo2;
+    uint32_t node;
+    float hi0, hi1, hi2;
+    uint32_t pad;
+};
+
+// open metric: identical to L2Distance::box_distance (kdtree.hpp:34-45)
+__device__ __forceinline__ float axis_lb_open(float lo, float hi, float q) {
+    float dl = fmaxf(__fsub_rn(lo, q), 0.0f);
+    float dr = fmaxf(__fsub_rn(q, hi), 0.0f);
+    return __fadd_rn(__fmul_rn(dl, dl), __fmul_rn(dr, dr));
+}
+
+// periodic metric: lower bound of min(d^2, (d+L)^2, (d-L)^2) over d = fl(p - q) in [a, b]
+// (a = fl(lo - q), b = fl(hi - q)): each image interval is the same monotone operation applied to
+// the end points, and the distance of an interval [u, v] from zero is max(u, -v, 0).
+__device__ __forceinline__ float axis_lb_periodic(float a, float b, float L) {
+    float v0 = fmaxf(fmaxf(a, -b), 0.0f);
+    float ap = __fadd_rn(a, L), bp = __fadd_rn(b, L);
+    float vp = fmaxf(fmaxf(ap, -bp), 0.0f);
+    float am = __fsub_rn(a, L), bm = __fsub_rn(b, L);
+    float vm = fmaxf(fmaxf(am, -bm), 0.0f);
+    float v = fminf(v0, fminf(vp, vm));
+    return __fmul_rn(v, v);
+}
+
+template <int K, bool PERIODIC>
+__global__ void __launch_bounds__(kQueryThreads)
+knn_packet_kernel(QueryTree t, const float *__restrict__ q_aos, const uint32_t *__restrict__ order,
+                  uint64_t m, int k_out, float *__restrict__ out_d, uint32_t *__restrict__ out_i) {
+    __shared__ StackEntry stack[kQueryWarps][kMaxStack];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t slot = (uint64_t)blockIdx.x * kQueryThreads + threadIdx.x;
+    const bool valid = slot < m;
+    if (!__any_sync(0xffffffffu, valid)) return;
+    const uint32_t qid = order[valid ? slot : m - 1];
+    const float qx = q_aos[3 * (uint64_t)qid], qy = q_aos[3 * (uint64_t)qid + 1],
+                qz = q_aos[3 * (uint64_t)qid + 2];
+    const float wrap_d2 = __fmul_rn(0.5f * t.box, 0.5f * t.box);
+
+    TopK<K> top;
+    top.init();
+
+    StackEntry *st = stack[warp];
+    if (lane == 0) st[0] = StackEntry{t.lo[0], t.lo[1], t.lo[2], 0u, t.hi[0], t.hi[1], t.hi[2], 0u};
+    __syncwarp();
+    int sp = 1;
+    while (sp > 0) {
+        --sp;
+        const StackEntry e = st[sp];
+        __syncwarp(); // everyone has read the entry before lane 0 overwrites the slot
+        float lb;
+        if (PERIODIC) {
+            // d = fl(p - q) of every point of the cell lies in [a, b] on each axis
+            lb = __fadd_rn(__fadd_rn(axis_lb_periodic(__fsub_rn(e.lo0, qx), __fsub_rn(e.hi0, qx), t.box),
+                                     axis_lb_periodic(__fsub_rn(e.lo1, qy), __fsub_rn(e.hi1, qy), t.box)),
+                           axis_lb_periodic(__fsub_rn(e.lo2, qz), __fsub_rn(e.hi2, qz), t.box));
+        } else {
+            lb = __fadd_rn(__fadd_rn(axis_lb_open(e.lo0, e.hi0, qx), axis_lb_open(e.lo1, e.hi1, qy)),
+                           axis_lb_open(e.lo2, e.hi2, qz));
+        }
+        // non-strict: an equal-distance point with a smaller index must still be found
+        const bool need = valid && lb <= top.worst();
+        const unsigned need_mask = __ballot_sync(0xffffffffu, need);
+        if (need_mask == 0u) continue;
+        const nbk_node nd = *reinterpret_cast<const nbk_node *>(
+            &reinterpret_cast<const int4 *>(t.nodes)[e.node]);
+        if (nd.dim < 0) {
+            scan_leaf<K, PERIODIC>(t, nd.left, nd.right, qx, qy, qz, wrap_d2, false, top);
+            continue;
+        }
+        const float qd = nd.dim == 0 ? qx : (nd.dim == 1 ? qy : qz);
+        const unsigned right_mask = __ballot_sync(0xffffffffu, need && qd > nd.split);
+        const bool right_first = 2 * __popc(right_mask) > __popc(need_mask);
+        if (lane == 0) {
+            StackEntry l = e, r = e;
+            l.node = nd.left;
+            r.node = nd.right;
+            if (nd.dim == 0) { l.hi0 = nd.split; r.lo0 = nd.split; }
+            else if (nd.dim == 1) { l.hi1 = nd.split; r.lo1 = nd.split; }
+            else { l.hi2 = nd.split; r.lo2 = nd.split; }
+            st[sp] = right_first ? l : r;     // visited second
+            st[sp + 1] = right_first ? r : l; // visited first
+        }
+        __syncwarp();
+        sp += 2;
+    }
+    if (valid) write_row<K>(top, qid, k_out, out_d, out_i);
 }
 
 // ---- KDTreeQueryStatistics: the reference's own traversal, one thread per query -----------------
@@ -519,8 +501,10 @@ stats_kernel(QueryTree t, const float *__restrict__ q_aos, uint64_t m, int k,
                 nv += 1;
                 if (nd.dim < 0) {
                     for (uint32_t p = nd.left; p < nd.right; ++p) {
-                        float d = PERIODIC ? d2_periodic(t.x[p], t.y[p], t.z[p], q[0], q[1], q[2], t.box)
-                                           : d2_open(t.x[p], t.y[p], t.z[p], q[0], q[1], q[2]);
+                        const float px = tile_coord(t.tiles, p, 0), py = tile_coord(t.tiles, p, 1),
+                                    pz = tile_coord(t.tiles, p, 2);
+                        float d = PERIODIC ? d2_periodic(px, py, pz, q[0], q[1], q[2], t.box)
+                                           : d2_open(px, py, pz, q[0], q[1], q[2]);
                         if (d < best[top]) {
                             best[top] = d;
                             top = 0;
@@ -553,7 +537,6 @@ stats_kernel(QueryTree t, const float *__restrict__ q_aos, uint64_t m, int k,
             }
         }
     }
-    // block reduction
     for (int o = 16; o > 0; o >>= 1) {
         nv += __shfl_xor_sync(0xffffffffu, nv, o);
         np += __shfl_xor_sync(0xffffffffu, np, o);
@@ -564,6 +547,19 @@ stats_kernel(QueryTree t, const float *__restrict__ q_aos, uint64_t m, int k,
         atomicAdd(&out3[1], np);
         atomicAdd(&out3[2], pv);
     }
+}
+
+// ---- tile -> SoA (backs nbk_tree_copy_points) -------------------------------------------------------
+__global__ void __launch_bounds__(256)
+untile_kernel(const float4 *__restrict__ tiles, uint64_t n, float *__restrict__ x,
+              float *__restrict__ y, float *__restrict__ z, uint32_t *__restrict__ idx) {
+    uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const float *f = reinterpret_cast<const float *>(tiles) + (i >> 3) * 32 + (i & 7);
+    x[i] = f[0];
+    y[i] = f[8];
+    z[i] = f[16];
+    idx[i] = __float_as_uint(f[24]);
 }
 
 } // namespace nbk

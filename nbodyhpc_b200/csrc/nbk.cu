@@ -30,18 +30,15 @@ struct DeviceGuard {
 constexpr uint64_t kAlign = 256;
 
 struct ArenaLayout {
-    uint64_t nodes, x, y, z, idx, total;
+    uint64_t nodes, tiles, total;
 };
 
+// [ nodes: n_nodes x 16 B | tiles: n_padded/8 x 128 B {x[8], y[8], z[8], idx[8]} ]
 inline ArenaLayout arena_layout(uint64_t n_padded, uint64_t n_nodes) {
     ArenaLayout l;
-    uint64_t col = align_up(std::max<uint64_t>(n_padded, 1) * 4, kAlign);
     l.nodes = 0;
-    l.x = align_up(n_nodes * sizeof(nbk_node), kAlign);
-    l.y = l.x + col;
-    l.z = l.y + col;
-    l.idx = l.z + col;
-    l.total = l.idx + col;
+    l.tiles = align_up(n_nodes * sizeof(nbk_node), kAlign);
+    l.total = l.tiles + align_up(std::max<uint64_t>(n_padded, 8) * 16, kAlign);
     return l;
 }
 } // namespace nbk
@@ -55,10 +52,7 @@ struct nbk_tree {
     void bind() {
         nbk::ArenaLayout l = nbk::arena_layout(meta.n_padded, meta.n_nodes);
         view.nodes = reinterpret_cast<nbk_node *>(arena + l.nodes);
-        view.x = reinterpret_cast<float *>(arena + l.x);
-        view.y = reinterpret_cast<float *>(arena + l.y);
-        view.z = reinterpret_cast<float *>(arena + l.z);
-        view.idx = reinterpret_cast<uint32_t *>(arena + l.idx);
+        view.tiles = reinterpret_cast<float *>(arena + l.tiles);
     }
     // periodic < 0: the tree's own metric
     nbk::QueryTree query_view(int periodic = -1, float box_size = 0.0f) const {
@@ -68,10 +62,7 @@ struct nbk_tree {
         }
         nbk::QueryTree q;
         q.nodes = view.nodes;
-        q.x = view.x;
-        q.y = view.y;
-        q.z = view.z;
-        q.idx = view.idx;
+        q.tiles = reinterpret_cast<const float4 *>(view.tiles);
         q.periodic = periodic != 0;
         q.box = periodic ? box_size : 0.0f;
         for (int d = 0; d < 3; ++d) {
@@ -246,26 +237,36 @@ inline bool use_packet_kernel() {
 }
 
 template <int K, bool P>
-void launch_packet(QueryTree const &qt, const float *d_q, const uint32_t *order, uint64_t m, int k,
-                   float *d_out_d, uint32_t *d_out_i, cudaStream_t stream) {
+void launch_knn(QueryTree const &qt, const float *d_q, const uint32_t *order, uint64_t m, int k,
+                float *d_out_d, uint32_t *d_out_i, DeferList defer, cudaStream_t stream) {
     unsigned grid = (unsigned)div_up(m, kQueryThreads);
-    if (use_packet_kernel())
+    if (use_packet_kernel()) {
         knn_packet_kernel<K, P><<<grid, kQueryThreads, 0, stream>>>(qt, d_q, order, m, k, d_out_d, d_out_i);
-    else
-        knn_lane_kernel<K, P><<<grid, kQueryThreads, 0, stream>>>(qt, d_q, order, m, k, d_out_d, d_out_i);
+        NBK_LAUNCHED();
+        return;
+    }
+    knn_lane_kernel<K, P, false><<<grid, kQueryThreads, 0, stream>>>(qt, d_q, order, m, k, d_out_d,
+                                                                      d_out_i, defer);
     NBK_LAUNCHED();
+    if (P) {
+        // queries whose search ball reaches through a face of the box (usually ~1 %): answered from
+        // scratch over all relevant image shifts; the kernel reads the count on the device
+        knn_lane_kernel<K, P, P><<<grid, kQueryThreads, 0, stream>>>(qt, d_q, order, m, k, d_out_d,
+                                                                    d_out_i, defer);
+        NBK_LAUNCHED();
+    }
 }
 
 template <bool P>
-void dispatch_packet(QueryTree const &qt, const float *d_q, const uint32_t *order, uint64_t m, int k,
-                     float *d_out_d, uint32_t *d_out_i, cudaStream_t stream) {
-    if (k <= 1) launch_packet<1, P>(qt, d_q, order, m, k, d_out_d, d_out_i, stream);
-    else if (k <= 2) launch_packet<2, P>(qt, d_q, order, m, k, d_out_d, d_out_i, stream);
-    else if (k <= 4) launch_packet<4, P>(qt, d_q, order, m, k, d_out_d, d_out_i, stream);
-    else if (k <= 8) launch_packet<8, P>(qt, d_q, order, m, k, d_out_d, d_out_i, stream);
-    else if (k <= 16) launch_packet<16, P>(qt, d_q, order, m, k, d_out_d, d_out_i, stream);
-    else if (k <= 32) launch_packet<32, P>(qt, d_q, order, m, k, d_out_d, d_out_i, stream);
-    else launch_packet<64, P>(qt, d_q, order, m, k, d_out_d, d_out_i, stream);
+void dispatch_knn(QueryTree const &qt, const float *d_q, const uint32_t *order, uint64_t m, int k,
+                  float *d_out_d, uint32_t *d_out_i, DeferList defer, cudaStream_t stream) {
+    if (k <= 1) launch_knn<1, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, stream);
+    else if (k <= 2) launch_knn<2, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, stream);
+    else if (k <= 4) launch_knn<4, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, stream);
+    else if (k <= 8) launch_knn<8, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, stream);
+    else if (k <= 16) launch_knn<16, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, stream);
+    else if (k <= 32) launch_knn<32, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, stream);
+    else launch_knn<64, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, stream);
 }
 
 constexpr int kMaxK = 64;
@@ -299,8 +300,15 @@ void query_device(nbk_tree const &tree, const float *d_q, uint64_t m, int k, flo
     const uint32_t *order = where ? vals_b : vals_a;
     t_order.finish();
     SectionTimer t_knn(NBK_SECTION_KNN_KERNEL, stream);
-    if (qt.periodic) dispatch_packet<true>(qt, d_q, order, m, k, d_out_d, d_out_i, stream);
-    else dispatch_packet<false>(qt, d_q, order, m, k, d_out_d, d_out_i, stream);
+    DeferList defer{nullptr, nullptr};
+    if (qt.periodic && !use_packet_kernel()) {
+        // the sort's input buffers are free again: reuse one as the deferred-query list
+        defer.slots = where ? keys_a : keys_b;
+        defer.count = scratch.get<uint32_t>(1);
+        NBK_CUDA(cudaMemsetAsync(defer.count, 0, 4, stream));
+    }
+    if (qt.periodic) dispatch_knn<true>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, stream);
+    else dispatch_knn<false>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, stream);
     t_knn.finish();
 }
 
@@ -444,11 +452,20 @@ int nbk_tree_copy_points(const nbk_tree *tree, float *x, float *y, float *z, uin
     return guarded([&] {
         if (!tree) throw Error(NBK_ERR_INVALID, "null argument");
         DeviceGuard guard(tree->device);
-        uint64_t bytes = tree->meta.n_padded * 4;
-        if (x) NBK_CUDA(cudaMemcpy(x, tree->view.x, bytes, cudaMemcpyDeviceToHost));
-        if (y) NBK_CUDA(cudaMemcpy(y, tree->view.y, bytes, cudaMemcpyDeviceToHost));
-        if (z) NBK_CUDA(cudaMemcpy(z, tree->view.z, bytes, cudaMemcpyDeviceToHost));
-        if (idx) NBK_CUDA(cudaMemcpy(idx, tree->view.idx, bytes, cudaMemcpyDeviceToHost));
+        const uint64_t n = tree->meta.n_padded;
+        if (n == 0) return;
+        cudaStream_t stream = nullptr;
+        Scratch scratch(stream);
+        float *dx = scratch.get<float>(n), *dy = scratch.get<float>(n), *dz = scratch.get<float>(n);
+        uint32_t *di = scratch.get<uint32_t>(n);
+        untile_kernel<<<(unsigned)div_up(n, 256), 256, 0, stream>>>(
+            reinterpret_cast<const float4 *>(tree->view.tiles), n, dx, dy, dz, di);
+        NBK_LAUNCHED();
+        if (x) NBK_CUDA(cudaMemcpyAsync(x, dx, n * 4, cudaMemcpyDeviceToHost, stream));
+        if (y) NBK_CUDA(cudaMemcpyAsync(y, dy, n * 4, cudaMemcpyDeviceToHost, stream));
+        if (z) NBK_CUDA(cudaMemcpyAsync(z, dz, n * 4, cudaMemcpyDeviceToHost, stream));
+        if (idx) NBK_CUDA(cudaMemcpyAsync(idx, di, n * 4, cudaMemcpyDeviceToHost, stream));
+        NBK_CUDA(cudaStreamSynchronize(stream));
     });
 }
 

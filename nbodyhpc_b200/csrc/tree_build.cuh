@@ -173,25 +173,26 @@ record_splits_kernel(const uint64_t *__restrict__ sorted_keys, const uint32_t *_
     nodes[nd].split = __uint_as_float(ordered_to_float(o));
 }
 
+// Final placement: point at leaf-order position i goes into tile i/8, slot i%8 of the arena's
+// 128-byte tiles {x[8], y[8], z[8], idx[8]} (see knn_query.cuh).
 __global__ void __launch_bounds__(256)
 gather_points_kernel(const float *__restrict__ x0, const float *__restrict__ y0,
                      const float *__restrict__ z0, const uint32_t *__restrict__ idx0,
-                     const uint32_t *__restrict__ perm, uint64_t n, float *__restrict__ x,
-                     float *__restrict__ y, float *__restrict__ z, uint32_t *__restrict__ idx) {
+                     const uint32_t *__restrict__ perm, uint64_t n, float *__restrict__ tiles) {
     uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
     uint32_t p = perm[i];
-    x[i] = x0[p];
-    y[i] = y0[p];
-    z[i] = z0[p];
-    idx[i] = idx0 ? idx0[p] : p;
+    float *f = tiles + (i >> 3) * 32 + (i & 7);
+    f[0] = x0[p];
+    f[8] = y0[p];
+    f[16] = z0[p];
+    f[24] = __uint_as_float(idx0 ? idx0[p] : p);
 }
 
 // ---- driver --------------------------------------------------------------------------------------
 struct TreeArena {
     nbk_node *nodes;
-    float *x, *y, *z;
-    uint32_t *idx;
+    float *tiles; // n_padded / 8 tiles of 32 floats
 };
 
 // Orders the points held in (x0,y0,z0[,idx0]) into the arena and fills the node array.
@@ -246,14 +247,14 @@ inline void build_levels(TopologyPlan const &plan, uint64_t n_padded, const floa
             NBK_LAUNCHED();
         }
         gather_points_kernel<<<grid, 256, 0, stream>>>(x0, y0, z0, idx0, perm_cur, n_padded,
-                                                       arena.x, arena.y, arena.z, arena.idx);
+                                                       arena.tiles);
         NBK_LAUNCHED();
         // the host tables must outlive the async copies
         NBK_CUDA(cudaStreamSynchronize(stream));
     } else {
         if (n_padded) {
             gather_points_kernel<<<grid, 256, 0, stream>>>(x0, y0, z0, idx0, perm, n_padded,
-                                                           arena.x, arena.y, arena.z, arena.idx);
+                                                           arena.tiles);
             NBK_LAUNCHED();
         }
         NBK_CUDA(cudaStreamSynchronize(stream));
