@@ -324,7 +324,7 @@ def run_b200_arm(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {
-            "bound": "hbm", "kernel": "knn_packet_kernel<8,periodic>", "achieved": achieved, "peak": peak,
+            "bound": "hbm", "kernel": "knn_lane_kernel<K=8,periodic> (primary pass; the boundary pass is included in the timed section)", "achieved": achieved, "peak": peak,
             "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
             "algorithmic_bytes_per_query": b_q, "queries_per_launch": m, "counters": counters_source,
             "kernel_ms_per_launch": knn_ms_per_launch, "kernel_share_of_step": knn_ms / total_ms,

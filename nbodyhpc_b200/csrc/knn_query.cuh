@@ -107,6 +107,15 @@ __device__ __forceinline__ void d2x4(float4 const &X, float4 const &Y, float4 co
     }
 }
 
+// Out of line on purpose: taken only for points more than L/2 away along some axis, and keeping it
+// out of the leaf loop keeps that loop's register footprint at the open-metric level.
+__device__ __noinline__ float4 d2x4_wrapped(float4 X, float4 Y, float4 Z, float qx, float qy, float qz,
+                                            float L) {
+    float d[4];
+    d2x4<true>(X, Y, Z, qx, qy, qz, L, d);
+    return make_float4(d[0], d[1], d[2], d[3]);
+}
+
 // ---- register-resident top-k ----------------------------------------------------------------------
 // keys sorted ascending; key = (d2 bits << 32) | index, held as two 32-bit halves.  d2 >= +0 so the
 // bit pattern orders like the float.  Empty slots hold (FLT_MAX, 0): a candidate at d2 == FLT_MAX
@@ -167,31 +176,40 @@ __device__ __forceinline__ void write_row(TopK<K> const &top, uint32_t qid, int 
 // an axis with |p - q| > L/2, i.e. when the open d2 is >= (L/2)^2 = wrap_d2; only then is the
 // 3-image formula evaluated.  `dedupe` is set while a shifted image is searched.
 template <int K, bool PERIODIC>
+__device__ __forceinline__ void scan_half_tile(const float4 *g, float qx, float qy, float qz, float L,
+                                               float wrap_d2, bool dedupe, TopK<K> &top) {
+    const float4 X = __ldg(g), Y = __ldg(g + 2), Z = __ldg(g + 4);
+    const uint4 I = __ldg(reinterpret_cast<const uint4 *>(g + 6));
+    float d[4];
+    d2x4<false>(X, Y, Z, qx, qy, qz, L, d);
+    if (PERIODIC) {
+        const float dmax = fmaxf(fmaxf(d[0], d[1]), fmaxf(d[2], d[3]));
+        if (dmax >= wrap_d2) {
+            const float4 w = d2x4_wrapped(X, Y, Z, qx, qy, qz, L);
+            d[0] = w.x; d[1] = w.y; d[2] = w.z; d[3] = w.w;
+        }
+    }
+    const float dmin = fminf(fminf(d[0], d[1]), fminf(d[2], d[3]));
+    if (dmin <= top.worst()) {
+        const uint32_t idx[4] = {I.x, I.y, I.z, I.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t chi = __float_as_uint(d[j]);
+            if (top.beats_worst(chi, idx[j]) && !(dedupe && top.contains(chi, idx[j])))
+                top.insert(chi, idx[j]);
+        }
+    }
+}
+
+template <int K, bool PERIODIC>
 __device__ __forceinline__ void scan_leaf(QueryTree const &t, uint32_t begin, uint32_t end, float qx,
                                           float qy, float qz, float wrap_d2, bool dedupe,
                                           TopK<K> &top) {
     const float4 *tp = t.tiles + (uint64_t)(begin >> 3) * kTileFloat4;
-    const uint32_t steps = (end - begin) >> 2;
-    for (uint32_t s = 0; s < steps; ++s) {
-        const float4 *g = tp + ((s >> 1) << 3) + (s & 1);
-        const float4 X = __ldg(g), Y = __ldg(g + 2), Z = __ldg(g + 4);
-        const uint4 I = __ldg(reinterpret_cast<const uint4 *>(g + 6));
-        float d[4];
-        d2x4<false>(X, Y, Z, qx, qy, qz, t.box, d);
-        if (PERIODIC) {
-            const float dmax = fmaxf(fmaxf(d[0], d[1]), fmaxf(d[2], d[3]));
-            if (dmax >= wrap_d2) d2x4<true>(X, Y, Z, qx, qy, qz, t.box, d);
-        }
-        const float dmin = fminf(fminf(d[0], d[1]), fminf(d[2], d[3]));
-        if (dmin <= top.worst()) {
-            const uint32_t idx[4] = {I.x, I.y, I.z, I.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t chi = __float_as_uint(d[j]);
-                if (top.beats_worst(chi, idx[j]) && !(dedupe && top.contains(chi, idx[j])))
-                    top.insert(chi, idx[j]);
-            }
-        }
+    const float4 *const te = t.tiles + (uint64_t)(end >> 3) * kTileFloat4;
+    for (; tp != te; tp += kTileFloat4) {
+        scan_half_tile<K, PERIODIC>(tp, qx, qy, qz, t.box, wrap_d2, dedupe, top);
+        scan_half_tile<K, PERIODIC>(tp + 1, qx, qy, qz, t.box, wrap_d2, dedupe, top);
     }
 }
 
@@ -229,7 +247,7 @@ __device__ __forceinline__ float min_shifted_root_term(float qx, float qy, float
 }
 
 #ifndef NBK_LANE_MIN_BLOCKS
-#define NBK_LANE_MIN_BLOCKS 8
+#define NBK_LANE_MIN_BLOCKS 9
 #endif
 
 struct DeferList {
@@ -277,6 +295,27 @@ knn_lane_kernel(QueryTree t, const float *__restrict__ q_aos, const uint32_t *__
     uint32_t cur = 0; // root
     bool done = !valid;
     uint32_t lbeg = 0, lend = 0;
+    uint32_t home = kNoNode; // first point of the leaf that was scanned up front
+
+    if (!IMAGES) {
+        // Home leaf first: plain descent to the leaf holding the query (no bounds, nothing pushed);
+        // the loop below scans it and only then starts the bounded traversal with a realistic k-th distance,
+        // so that almost none of the ~log2(N/leaf) far children on the path is ever pushed.
+        if (valid) {
+            uint32_t nd = 0;
+            while (true) {
+                const int4 raw = __ldg(reinterpret_cast<const int4 *>(t.nodes) + nd);
+                if (raw.x < 0) {
+                    lbeg = (uint32_t)raw.z;
+                    lend = (uint32_t)raw.w;
+                    break;
+                }
+                const float qd = raw.x == 0 ? qx : (raw.x == 1 ? qy : qz);
+                nd = __fsub_rn(__int_as_float(raw.y), qd) < 0.0f ? (uint32_t)raw.w : (uint32_t)raw.z;
+            }
+            home = lbeg; // the main loop scans [lbeg, lend) first, then starts at the root
+        }
+    }
 
     while (true) {
         // ---- walk until this lane has a leaf to scan (or is finished) -------------------------
@@ -316,9 +355,10 @@ knn_lane_kernel(QueryTree t, const float *__restrict__ q_aos, const uint32_t *__
             const int4 raw = __ldg(reinterpret_cast<const int4 *>(t.nodes) + cur);
             const int dim = raw.x;
             if (dim < 0) {
+                cur = kNoNode;
+                if (!IMAGES && (uint32_t)raw.z == home) continue; // already scanned
                 lbeg = (uint32_t)raw.z;
                 lend = (uint32_t)raw.w;
-                cur = kNoNode;
                 break;
             }
             const float split = __int_as_float(raw.y);

@@ -20,20 +20,29 @@ for r in rows[2:]:
         if any(h == k or (k in h and k in ("local_load", "local_store")) for k in KEYS) or "average_warps_issue_stalled" in h and "per_issue_active" in h:
             print(f"  {h:80s} {u:14s} {v}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(src)))
-hdr = rows[1]; data = [r for r in rows[2:] if len(r) == len(hdr)]
-ia, isrc, isamp, ithr = hdr.index("Instructions Executed"), hdr.index("Source"), hdr.index("# Samples"), hdr.index("Avg. Threads Executed")
-tot = sum(int(r[ia]) for r in data); stot = sum(int(r[isamp]) for r in data)
-print(f"SASS: {len(data)} instructions, {tot} warp-inst executed = {tot/units:.1f} per unit, {stot} samples")
-blocks, cur = [], None
-for n, r in enumerate(data):
-    c = int(r[ia]); op = r[isrc].split()
-    op = op[1] if op and op[0].startswith("@") and len(op) > 1 else (op[0] if op else "")
-    if cur and abs(c - cur["c"]) <= 0.02 * max(c, cur["c"]) + 1:
-        cur["n1"] = n; cur["tot"] += c; cur["samp"] += int(r[isamp]); cur["ops"].append(op); cur["thr"] += float(r[ithr]) * c
-    else:
-        cur = dict(n0=n, n1=n, c=c, tot=c, samp=int(r[isamp]), thr=float(r[ithr]) * c, ops=[op]); blocks.append(cur)
-print("  [sass range]  exec/unit  ninst  share_inst share_samples avg_threads  top opcodes")
-for b in blocks:
-    if b["tot"] > 0.004 * tot or b["samp"] > 0.004 * stot:
-        print(f"  [{b['n0']:4d}-{b['n1']:4d}] {b['c']/units:9.3f} {b['n1']-b['n0']+1:5d} {100*b['tot']/tot:8.1f}% {100*b['samp']/stot:8.1f}% {b['thr']/max(b['tot'],1):8.1f}   {Counter(b['ops']).most_common(6)}")
+allrows = list(csv.reader(io.StringIO(src)))
+sections, cur_sec = [], None
+for r in allrows:
+    if r and r[0] == "Kernel Name":
+        cur_sec = {"name": r[1] if len(r) > 1 else "", "hdr": None, "rows": []}; sections.append(cur_sec)
+    elif cur_sec is not None and cur_sec["hdr"] is None:
+        cur_sec["hdr"] = r
+    elif cur_sec is not None and len(r) == len(cur_sec["hdr"]):
+        cur_sec["rows"].append(r)
+for sec in sections:
+    hdr, data = sec["hdr"], sec["rows"]
+    ia, isrc, isamp, ithr = hdr.index("Instructions Executed"), hdr.index("Source"), hdr.index("# Samples"), hdr.index("Avg. Threads Executed")
+    tot = sum(int(r[ia]) for r in data); stot = sum(int(r[isamp]) for r in data)
+    print(f"SASS of {sec['name'][:60]}: {len(data)} instructions, {tot} warp-inst executed = {tot/units:.1f} per unit, {stot} samples")
+    blocks, cur = [], None
+    for n, r in enumerate(data):
+        c = int(r[ia]); op = r[isrc].split()
+        op = op[1] if op and op[0].startswith("@") and len(op) > 1 else (op[0] if op else "")
+        if cur and abs(c - cur["c"]) <= 0.02 * max(c, cur["c"]) + 1:
+            cur["n1"] = n; cur["tot"] += c; cur["samp"] += int(r[isamp]); cur["ops"].append(op); cur["thr"] += float(r[ithr]) * c
+        else:
+            cur = dict(n0=n, n1=n, c=c, tot=c, samp=int(r[isamp]), thr=float(r[ithr]) * c, ops=[op]); blocks.append(cur)
+    print("  [sass range]  exec/unit  ninst  share_inst share_samples avg_threads  top opcodes")
+    for b in blocks:
+        if b["tot"] > 0.004 * tot or b["samp"] > 0.004 * max(stot, 1):
+            print(f"  [{b['n0']:4d}-{b['n1']:4d}] {b['c']/units:9.3f} {b['n1']-b['n0']+1:5d} {100*b['tot']/max(tot,1):8.1f}% {100*b['samp']/max(stot,1):8.1f}% {b['thr']/max(b['tot'],1):8.1f}   {Counter(b['ops']).most_common(6)}")
