@@ -139,6 +139,21 @@ template <int K> struct TopK {
         for (int j = 0; j < K; ++j) hit = hit || (hi[j] == chi && lo[j] == clo);
         return hit;
     }
+    static constexpr int kSize = K;
+    static constexpr bool kShared = false;
+    __device__ __forceinline__ void bind(unsigned long long *) {}
+    __device__ __forceinline__ void write_row(uint32_t qid, int k_out, float *__restrict__ out_d,
+                                              uint32_t *__restrict__ out_i) const {
+        float *od = out_d + (uint64_t)qid * k_out;
+        uint32_t *oi = out_i + (uint64_t)qid * k_out;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            if (j < k_out) {
+                od[j] = __fsqrt_rn(__uint_as_float(hi[j])); // postprocess, kdtree.cpp:154-156
+                oi[j] = hi[j] == kFltMaxBits ? 0xFFFFFFFFu : lo[j];
+            }
+        }
+    }
     // precondition: beats_worst(chi, clo).  One 64-bit compare (2 instructions) + 4 selects per step.
     __device__ __forceinline__ void insert(uint32_t chi, uint32_t clo) {
         hi[K - 1] = chi;
@@ -157,27 +172,88 @@ template <int K> struct TopK {
     }
 };
 
-template <int K>
-__device__ __forceinline__ void write_row(TopK<K> const &top, uint32_t qid, int k_out,
-                                          float *__restrict__ out_d, uint32_t *__restrict__ out_i) {
-    float *od = out_d + (uint64_t)qid * k_out;
-    uint32_t *oi = out_i + (uint64_t)qid * k_out;
-#pragma unroll
-    for (int j = 0; j < K; ++j) {
-        if (j < k_out) {
-            od[j] = __fsqrt_rn(__uint_as_float(top.hi[j])); // postprocess, kdtree.cpp:154-156
-            oi[j] = top.hi[j] == kFltMaxBits ? 0xFFFFFFFFu : top.lo[j];
+// ---- shared-memory top-k for large k ----------------------------------------------------------------
+// For k > 16 a sorted register list costs O(k) per insertion and most of the register file.  This
+// variant keeps each lane's k best in a binary MAX-heap in shared memory, slot-major
+// (heap[slot * blockDim + thread]: any per-lane slot pattern is bank-conflict free), so that
+// replacing the current worst costs O(log k) like the reference's tournament tree
+// (tournament_tree.hpp:49-91); the root (= current k-th best) is mirrored in registers.  The row is
+// produced by a heap sort in the epilogue.
+template <int K> struct HeapK {
+    static constexpr int kSize = K;
+    static constexpr bool kShared = true;
+    unsigned long long *heap; // this thread's column
+    uint32_t stride;
+    uint32_t rhi, rlo;         // root
+    __device__ __forceinline__ void bind(unsigned long long *base) {
+        heap = base + threadIdx.x;
+        stride = blockDim.x;
+    }
+    __device__ __forceinline__ unsigned long long &at(int slot) const { return heap[(uint32_t)slot * stride]; }
+    __device__ __forceinline__ void init() {
+        for (int j = 0; j < K; ++j) at(j) = (unsigned long long)kFltMaxBits << 32;
+        rhi = kFltMaxBits;
+        rlo = 0u;
+    }
+    __device__ __forceinline__ float worst() const { return __uint_as_float(rhi); }
+    __device__ __forceinline__ bool beats_worst(uint32_t chi, uint32_t clo) const {
+        return chi < rhi || (chi == rhi && clo < rlo);
+    }
+    __device__ __forceinline__ bool contains(uint32_t chi, uint32_t clo) const {
+        const unsigned long long c = ((unsigned long long)chi << 32) | clo;
+        bool hit = false;
+        for (int j = 0; j < K; ++j) hit = hit || at(j) == c;
+        return hit;
+    }
+    // sift `c` down from the root of a heap of `size` slots
+    __device__ __forceinline__ void sift_down(unsigned long long c, int size) {
+        int i = 0;
+        while (true) {
+            const int l = 2 * i + 1;
+            if (l >= size) break;
+            const int r = l + 1;
+            const unsigned long long kl = at(l);
+            const unsigned long long kr = r < size ? at(r) : 0ull;
+            const bool right = kr > kl;
+            const unsigned long long kb = right ? kr : kl;
+            if (kb <= c) break;
+            at(i) = kb;
+            i = right ? r : l;
+        }
+        at(i) = c;
+    }
+    // precondition: beats_worst(chi, clo): the root (current worst) is replaced
+    __device__ __forceinline__ void insert(uint32_t chi, uint32_t clo) {
+        sift_down(((unsigned long long)chi << 32) | clo, K);
+        const unsigned long long root = at(0);
+        rhi = (uint32_t)(root >> 32);
+        rlo = (uint32_t)root;
+    }
+    __device__ __forceinline__ void write_row(uint32_t qid, int k_out, float *__restrict__ out_d,
+                                              uint32_t *__restrict__ out_i) {
+        float *od = out_d + (uint64_t)qid * k_out;
+        uint32_t *oi = out_i + (uint64_t)qid * k_out;
+        // heap sort: the maximum leaves first and lands at the end of the row
+        for (int size = K; size > 0; --size) {
+            const unsigned long long top = at(0);
+            const int j = size - 1;
+            if (j < k_out) {
+                const uint32_t h = (uint32_t)(top >> 32);
+                od[j] = __fsqrt_rn(__uint_as_float(h)); // postprocess, kdtree.cpp:154-156
+                oi[j] = h == kFltMaxBits ? 0xFFFFFFFFu : (uint32_t)top;
+            }
+            if (size > 1) sift_down(at(size - 1), size - 1);
         }
     }
-}
+};
 
 // Scans the tiles [begin, end) of one leaf for this lane's query.  Per 4 points: x, y, z and the
 // indices are four 16-byte loads from one 128-byte tile.  PERIODIC: a wrapped image can only win on
 // an axis with |p - q| > L/2, i.e. when the open d2 is >= (L/2)^2 = wrap_d2; only then is the
 // 3-image formula evaluated.  `dedupe` is set while a shifted image is searched.
-template <int K, bool PERIODIC>
+template <typename Top, bool PERIODIC>
 __device__ __forceinline__ void scan_half_tile(const float4 *g, float qx, float qy, float qz, float L,
-                                               float wrap_d2, bool dedupe, TopK<K> &top) {
+                                               float wrap_d2, bool dedupe, Top &top) {
     const float4 X = __ldg(g), Y = __ldg(g + 2), Z = __ldg(g + 4);
     const uint4 I = __ldg(reinterpret_cast<const uint4 *>(g + 6));
     float d[4];
@@ -201,15 +277,14 @@ __device__ __forceinline__ void scan_half_tile(const float4 *g, float qx, float 
     }
 }
 
-template <int K, bool PERIODIC>
+template <typename Top, bool PERIODIC>
 __device__ __forceinline__ void scan_leaf(QueryTree const &t, uint32_t begin, uint32_t end, float qx,
-                                          float qy, float qz, float wrap_d2, bool dedupe,
-                                          TopK<K> &top) {
+                                          float qy, float qz, float wrap_d2, bool dedupe, Top &top) {
     const float4 *tp = t.tiles + (uint64_t)(begin >> 3) * kTileFloat4;
     const float4 *const te = t.tiles + (uint64_t)(end >> 3) * kTileFloat4;
     for (; tp != te; tp += kTileFloat4) {
-        scan_half_tile<K, PERIODIC>(tp, qx, qy, qz, t.box, wrap_d2, dedupe, top);
-        scan_half_tile<K, PERIODIC>(tp + 1, qx, qy, qz, t.box, wrap_d2, dedupe, top);
+        scan_half_tile<Top, PERIODIC>(tp, qx, qy, qz, t.box, wrap_d2, dedupe, top);
+        scan_half_tile<Top, PERIODIC>(tp + 1, qx, qy, qz, t.box, wrap_d2, dedupe, top);
     }
 }
 
@@ -255,8 +330,8 @@ struct DeferList {
     uint32_t *count;
 };
 
-template <int K, bool PERIODIC, bool IMAGES>
-__global__ void __launch_bounds__(kQueryThreads, IMAGES ? 1 : NBK_LANE_MIN_BLOCKS)
+template <typename Top, bool PERIODIC, bool IMAGES>
+__global__ void __launch_bounds__(kQueryThreads, (IMAGES || Top::kShared) ? 1 : NBK_LANE_MIN_BLOCKS)
 knn_lane_kernel(QueryTree t, const float *__restrict__ q_aos, const uint32_t *__restrict__ order,
                 uint64_t m, int k_out, float *__restrict__ out_d, uint32_t *__restrict__ out_i,
                 DeferList defer) {
@@ -279,7 +354,9 @@ knn_lane_kernel(QueryTree t, const float *__restrict__ q_aos, const uint32_t *__
     const float L = t.box;
     const float wrap_d2 = __fmul_rn(0.5f * L, 0.5f * L);
 
-    TopK<K> top;
+    extern __shared__ unsigned long long heap_smem[];
+    Top top;
+    top.bind(heap_smem);
     top.init();
 
     float4 stack[kLaneStack]; // (t0, t1, t2, node bits)
@@ -378,7 +455,7 @@ knn_lane_kernel(QueryTree t, const float *__restrict__ q_aos, const uint32_t *__
         }
         if (!__any_sync(0xffffffffu, lbeg != lend)) break;
         // ---- scan it ------------------------------------------------------------------------------
-        scan_leaf<K, PERIODIC>(t, lbeg, lend, qx, qy, qz, wrap_d2, IMAGES && img > 0, top);
+        scan_leaf<Top, PERIODIC>(t, lbeg, lend, qx, qy, qz, wrap_d2, IMAGES && img > 0, top);
         lbeg = lend = 0;
     }
 
@@ -389,7 +466,7 @@ knn_lane_kernel(QueryTree t, const float *__restrict__ q_aos, const uint32_t *__
             return;
         }
     }
-    write_row<K>(top, qid, k_out, out_d, out_i);
+    top.write_row(qid, k_out, out_d, out_i);
 }
 
 // ---- the packet kernel -----------------------------------------------------------------------------
@@ -464,7 +541,7 @@ knn_packet_kernel(QueryTree t, const float *__restrict__ q_aos, const uint32_t *
         const nbk_node nd = *reinterpret_cast<const nbk_node *>(
             &reinterpret_cast<const int4 *>(t.nodes)[e.node]);
         if (nd.dim < 0) {
-            scan_leaf<K, PERIODIC>(t, nd.left, nd.right, qx, qy, qz, wrap_d2, false, top);
+            scan_leaf<TopK<K>, PERIODIC>(t, nd.left, nd.right, qx, qy, qz, wrap_d2, false, top);
             continue;
         }
         const float qd = nd.dim == 0 ? qx : (nd.dim == 1 ? qy : qz);
@@ -483,7 +560,7 @@ knn_packet_kernel(QueryTree t, const float *__restrict__ q_aos, const uint32_t *
         __syncwarp();
         sp += 2;
     }
-    if (valid) write_row<K>(top, qid, k_out, out_d, out_i);
+    if (valid) top.write_row(qid, k_out, out_d, out_i);
 }
 
 // ---- KDTreeQueryStatistics: the reference's own traversal, one thread per query -----------------

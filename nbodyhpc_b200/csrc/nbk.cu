@@ -158,6 +158,15 @@ std::unique_ptr<nbk_tree> finish_build(uint64_t n, uint64_t n_padded, int leaf_s
     uint32_t b[6];
     NBK_CUDA(cudaMemcpyAsync(b, d_bounds6, sizeof b, cudaMemcpyDeviceToHost, stream));
     NBK_CUDA(cudaStreamSynchronize(stream));
+    {
+        // hand the build's scratch (several times the tree size) back to the device; queries keep
+        // their own, much smaller, working set cached in the pool afterwards
+        cudaMemPool_t pool;
+        int dev = 0;
+        NBK_CUDA(cudaGetDevice(&dev));
+        NBK_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        NBK_CUDA(cudaMemPoolTrimTo(pool, 0));
+    }
     for (int d = 0; d < 3; ++d) {
         bool empty = b[d] == 0xFFFFFFFFu && b[3 + d] == 0u;
         uint32_t lo = ordered_to_float(b[d]), hi = ordered_to_float(b[3 + d]);
@@ -236,25 +245,52 @@ inline bool use_packet_kernel() {
     return packet;
 }
 
-template <int K, bool P>
-void launch_knn(QueryTree const &qt, const float *d_q, const uint32_t *order, uint64_t m, int k,
-                float *d_out_d, uint32_t *d_out_i, DeferList defer, cudaStream_t stream) {
+// k <= 8: sorted register list; above: shared-memory heap (NBK_HEAP_FROM overrides the threshold)
+inline int heap_from_k() {
+    static const int v = [] {
+        const char *e = std::getenv("NBK_HEAP_FROM");
+        return e ? std::atoi(e) : 9;
+    }();
+    return v;
+}
+
+template <typename Top, bool P>
+void launch_lane(QueryTree const &qt, const float *d_q, const uint32_t *order, uint64_t m, int k,
+                 float *d_out_d, uint32_t *d_out_i, DeferList defer, cudaStream_t stream) {
     unsigned grid = (unsigned)div_up(m, kQueryThreads);
-    if (use_packet_kernel()) {
-        knn_packet_kernel<K, P><<<grid, kQueryThreads, 0, stream>>>(qt, d_q, order, m, k, d_out_d, d_out_i);
-        NBK_LAUNCHED();
-        return;
+    size_t smem = Top::kShared ? (size_t)Top::kSize * kQueryThreads * sizeof(unsigned long long) : 0;
+    auto fast = knn_lane_kernel<Top, P, false>;
+    auto general = knn_lane_kernel<Top, P, P>;
+    if (smem > 48 * 1024) {
+        NBK_CUDA(cudaFuncSetAttribute(fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NBK_CUDA(cudaFuncSetAttribute(general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    knn_lane_kernel<K, P, false><<<grid, kQueryThreads, 0, stream>>>(qt, d_q, order, m, k, d_out_d,
-                                                                      d_out_i, defer);
+    fast<<<grid, kQueryThreads, smem, stream>>>(qt, d_q, order, m, k, d_out_d, d_out_i, defer);
     NBK_LAUNCHED();
     if (P) {
         // queries whose search ball reaches through a face of the box (usually ~1 %): answered from
         // scratch over all relevant image shifts; the kernel reads the count on the device
-        knn_lane_kernel<K, P, P><<<grid, kQueryThreads, 0, stream>>>(qt, d_q, order, m, k, d_out_d,
-                                                                    d_out_i, defer);
+        general<<<grid, kQueryThreads, smem, stream>>>(qt, d_q, order, m, k, d_out_d, d_out_i, defer);
         NBK_LAUNCHED();
     }
+}
+
+template <int K, bool P>
+void launch_knn(QueryTree const &qt, const float *d_q, const uint32_t *order, uint64_t m, int k,
+                float *d_out_d, uint32_t *d_out_i, DeferList defer, cudaStream_t stream) {
+    if (use_packet_kernel()) {
+        unsigned grid = (unsigned)div_up(m, kQueryThreads);
+        knn_packet_kernel<K, P><<<grid, kQueryThreads, 0, stream>>>(qt, d_q, order, m, k, d_out_d, d_out_i);
+        NBK_LAUNCHED();
+        return;
+    }
+    if constexpr (K >= 16) {
+        if (k >= heap_from_k()) {
+            launch_lane<HeapK<K>, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, stream);
+            return;
+        }
+    }
+    launch_lane<TopK<K>, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, stream);
 }
 
 template <bool P>
