@@ -131,7 +131,8 @@ std::unique_ptr<nbk_tree> alloc_tree(nbk_tree_meta const &meta, int device) {
     (void)device;
     ArenaLayout l = arena_layout(meta.n_padded, meta.n_nodes);
     t->meta.arena_bytes = l.total;
-    NBK_CUDA(cudaMalloc(&t->arena, l.total));
+    // from the stream-ordered pool (legacy stream): a tree freed and rebuilt reuses the same memory
+    NBK_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&t->arena), l.total, nullptr));
     t->bind();
     return t;
 }
@@ -139,33 +140,48 @@ std::unique_ptr<nbk_tree> alloc_tree(nbk_tree_meta const &meta, int device) {
 // Common tail of the three build entry points.  (x0,y0,z0[,idx0]) are device SoA columns of
 // n_padded points, perm holds the identity, bounds6 the orderable bounding box.
 std::unique_ptr<nbk_tree> finish_build(uint64_t n, uint64_t n_padded, int leaf_size, int block_size,
-                                       int periodic, float box_size, const float *x0,
-                                       const float *y0, const float *z0, const uint32_t *idx0,
+                                       int periodic, float box_size, float *x0, float *y0, float *z0,
+                                       const uint32_t *idx0,
                                        uint32_t *perm, const uint32_t *d_bounds6, int device,
                                        cudaStream_t stream) {
-    TopologyPlan plan = plan_topology(n_padded, leaf_size, block_size);
+    // NBK_BUILD=sort selects the per-level radix-sort build (cross-check); default: select + partition
+    static const bool sort_build = [] {
+        const char *v = std::getenv("NBK_BUILD");
+        return v && std::string(v) == "sort";
+    }();
+    td::TopPlan top = td::plan_top(n_padded, leaf_size, block_size);
     nbk_tree_meta meta{};
     meta.n_points = n;
     meta.n_padded = n_padded;
-    meta.n_nodes = plan.nodes.size();
+    meta.n_nodes = top.n_nodes;
     meta.leaf_size = leaf_size;
     meta.block_size = block_size;
     meta.periodic = periodic ? 1 : 0;
     meta.box_size = periodic ? box_size : 0.0f;
-    meta.n_levels = (int)plan.levels.size();
+    meta.n_levels = top.n_levels;
     auto tree = alloc_tree(meta, device);
-    build_levels(plan, n_padded, x0, y0, z0, idx0, perm, tree->view, stream);
+    if (sort_build) {
+        TopologyPlan plan = plan_topology(n_padded, leaf_size, block_size);
+        build_levels(plan, n_padded, x0, y0, z0, idx0, perm, tree->view, stream);
+    } else {
+        build_select(top, n_padded, leaf_size, block_size, x0, y0, z0, perm, idx0, d_bounds6,
+                     tree->view, stream);
+    }
     uint32_t b[6];
     NBK_CUDA(cudaMemcpyAsync(b, d_bounds6, sizeof b, cudaMemcpyDeviceToHost, stream));
     NBK_CUDA(cudaStreamSynchronize(stream));
     {
-        // hand the build's scratch (several times the tree size) back to the device; queries keep
-        // their own, much smaller, working set cached in the pool afterwards
+        // A big build's scratch (several times the tree) goes back to the device so that query outputs
+        // can use it; small ones stay cached in the pool, which makes the next build allocation-free.
         cudaMemPool_t pool;
         int dev = 0;
         NBK_CUDA(cudaGetDevice(&dev));
         NBK_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
-        NBK_CUDA(cudaMemPoolTrimTo(pool, 0));
+        uint64_t reserved = 0;
+        size_t free_b = 0, total_b = 0;
+        NBK_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved));
+        NBK_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        if (reserved > total_b / 8) NBK_CUDA(cudaMemPoolTrimTo(pool, 0));
     }
     for (int d = 0; d < 3; ++d) {
         bool empty = b[d] == 0xFFFFFFFFu && b[3 + d] == 0u;
@@ -191,7 +207,7 @@ std::unique_ptr<nbk_tree> build_from_device_aos(const float *d_aos, uint64_t n, 
     const uint32_t init[8] = {0u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u, 0u};
     NBK_CUDA(cudaMemcpyAsync(aux, init, sizeof init, cudaMemcpyHostToDevice, stream));
     if (n_padded) {
-        ingest_aos_kernel<<<(unsigned)div_up(n_padded, 256), 256, 0, stream>>>(
+        ingest_aos_kernel<<<(unsigned)std::min<uint64_t>(div_up(n_padded, 256), 148 * 16), 256, 0, stream>>>(
             d_aos, n, n_padded, x0, y0, z0, perm, periodic, box_size, aux, aux + 1);
         NBK_LAUNCHED();
     }
@@ -431,7 +447,7 @@ nbk_tree *nbk_tree_build_soa(const float *x, const float *y, const float *z, con
         NBK_CUDA(cudaMemcpyAsync(z0, z, n_padded * 4, cudaMemcpyHostToDevice, stream));
         NBK_CUDA(cudaMemcpyAsync(idx0, idx, n_padded * 4, cudaMemcpyHostToDevice, stream));
         if (n_padded) {
-            scan_soa_kernel<<<(unsigned)div_up(n_padded, 256), 256, 0, stream>>>(x0, y0, z0, n_padded,
+            scan_soa_kernel<<<(unsigned)std::min<uint64_t>(div_up(n_padded, 256), 148 * 16), 256, 0, stream>>>(x0, y0, z0, n_padded,
                                                                                perm, aux + 1);
             NBK_LAUNCHED();
         }
@@ -461,7 +477,8 @@ void nbk_tree_free(nbk_tree *tree) {
     int prev = -1;
     cudaGetDevice(&prev);
     cudaSetDevice(tree->device);
-    cudaFree(tree->arena);
+    cudaDeviceSynchronize(); // queries may still be running on caller streams (cudaFree used to imply this)
+    cudaFreeAsync(tree->arena, nullptr);
     if (prev >= 0) cudaSetDevice(prev);
     delete tree;
 }

@@ -14,6 +14,8 @@
 
 #include "common.cuh"
 #include "radix_sort.cuh"
+#include "tree_bottom.cuh"
+#include "tree_topdown.cuh"
 
 namespace nbk {
 
@@ -63,84 +65,101 @@ inline TopologyPlan plan_topology(uint64_t n_padded, int leaf_size, int block_si
 
 // ---- kernels -------------------------------------------------------------------------------------
 
-// AoS (n,3) -> SoA columns padded with FLT_MAX to n_padded, identity permutation, segment 0
+// Block-wide min/max of the orderable coordinates of the real points, then ONE atomic per block and
+// value (a per-warp atomic on six addresses serialises the whole grid on them).
+__device__ __forceinline__ void block_bounds(uint32_t (&lo)[3], uint32_t (&hi)[3], uint32_t *bounds6) {
+    __shared__ uint32_t s_b[6][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            lo[d] = min(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], s));
+            hi[d] = max(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], s));
+        }
+        if (lane == 0) {
+            s_b[d][warp] = lo[d];
+            s_b[3 + d][warp] = hi[d];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        const bool is_min = threadIdx.x < 3;
+        uint32_t v = is_min ? 0xFFFFFFFFu : 0u;
+        for (int w = 0; w < 8; ++w) v = is_min ? min(v, s_b[threadIdx.x][w]) : max(v, s_b[threadIdx.x][w]);
+        if (is_min ? v != 0xFFFFFFFFu : v != 0u) {
+            if (is_min) atomicMin(&bounds6[threadIdx.x], v);
+            else atomicMax(&bounds6[threadIdx.x], v);
+        }
+    }
+}
+
+// AoS (n,3) -> SoA columns padded with FLT_MAX to n_padded, identity permutation
 // (pybind.cpp:14-56).  flags[0] |= 1 if a coordinate is outside [0, box] (periodic only);
-// bounds6 = {min x,y,z, max x,y,z} of the real points as orderable uint32.
+// bounds6 = {min x,y,z, max x,y,z} of the real points as orderable uint32.  Grid-stride.
 __global__ void __launch_bounds__(256)
 ingest_aos_kernel(const float *__restrict__ aos, uint64_t n, uint64_t n_padded,
                   float *__restrict__ x, float *__restrict__ y, float *__restrict__ z,
                   uint32_t *__restrict__ perm, int periodic, float box, uint32_t *flags,
                   uint32_t *bounds6) {
     __shared__ float tile[256 * 3];
-    uint64_t base = (uint64_t)blockIdx.x * 256;
-    uint64_t in_tile = n > base ? (n - base < 256 ? n - base : 256) : 0;
-    for (uint32_t j = threadIdx.x; j < in_tile * 3; j += 256) tile[j] = aos[base * 3 + j];
-    __syncthreads();
-    uint64_t i = base + threadIdx.x;
-    float px = FLT_MAX, py = FLT_MAX, pz = FLT_MAX;
-    bool real = i < n;
-    if (real) {
-        px = tile[threadIdx.x * 3];
-        py = tile[threadIdx.x * 3 + 1];
-        pz = tile[threadIdx.x * 3 + 2];
+    uint32_t lo[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, hi[3] = {0u, 0u, 0u};
+    bool bad = false;
+    for (uint64_t base = (uint64_t)blockIdx.x * 256; base < n_padded; base += (uint64_t)gridDim.x * 256) {
+        const uint64_t in_tile = n > base ? (n - base < 256 ? n - base : 256) : 0;
+        for (uint32_t j = threadIdx.x; j < in_tile * 3; j += 256) tile[j] = aos[base * 3 + j];
+        __syncthreads();
+        const uint64_t i = base + threadIdx.x;
+        float px = FLT_MAX, py = FLT_MAX, pz = FLT_MAX;
+        const bool real = i < n;
+        if (real) {
+            px = tile[threadIdx.x * 3];
+            py = tile[threadIdx.x * 3 + 1];
+            pz = tile[threadIdx.x * 3 + 2];
+        }
+        __syncthreads();
+        if (i < n_padded) {
+            x[i] = px;
+            y[i] = py;
+            z[i] = pz;
+            perm[i] = (uint32_t)i;
+        }
+        bad = bad || (real && periodic &&
+                      !(px >= 0.0f && px <= box && py >= 0.0f && py <= box && pz >= 0.0f && pz <= box));
+        if (real) {
+            const float p[3] = {px, py, pz};
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const uint32_t o = float_to_ordered(__float_as_uint(p[d]));
+                lo[d] = min(lo[d], o);
+                hi[d] = max(hi[d], o);
+            }
+        }
     }
-    if (i < n_padded) {
-        x[i] = px;
-        y[i] = py;
-        z[i] = pz;
-        perm[i] = (uint32_t)i;
-    }
-    bool bad = real && periodic &&
-               !(px >= 0.0f && px <= box && py >= 0.0f && py <= box && pz >= 0.0f && pz <= box);
     if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flags, 1u);
-    // bounding box of the real points (warp reduce, then one atomic per warp)
-    uint32_t lo[3], hi[3];
-    const float p[3] = {px, py, pz};
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        uint32_t o = float_to_ordered(__float_as_uint(p[d]));
-        lo[d] = real ? o : 0xFFFFFFFFu;
-        hi[d] = real ? o : 0u;
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) {
-            lo[d] = min(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], s));
-            hi[d] = max(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], s));
-        }
-    }
-    if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            if (lo[d] != 0xFFFFFFFFu) atomicMin(&bounds6[d], lo[d]);
-            if (hi[d] != 0u) atomicMax(&bounds6[3 + d], hi[d]);
-        }
-    }
+    block_bounds(lo, hi, bounds6);
 }
 
-// Bounding box + periodic validation for a tree handed over as SoA columns.
+// Bounding box + identity permutation for a tree handed over as SoA columns.  Grid-stride.
 __global__ void __launch_bounds__(256)
 scan_soa_kernel(const float *__restrict__ x, const float *__restrict__ y,
                 const float *__restrict__ z, uint64_t n, uint32_t *__restrict__ perm,
                 uint32_t *bounds6) {
-    uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
-    bool in = i < n;
-    float p[3] = {in ? x[i] : 0.f, in ? y[i] : 0.f, in ? z[i] : 0.f};
-    if (in) perm[i] = (uint32_t)i;
-    // padding points (FLT_MAX) do not belong to the bounding box
-    bool real = in && !(p[0] == FLT_MAX && p[1] == FLT_MAX && p[2] == FLT_MAX);
+    uint32_t lo[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, hi[3] = {0u, 0u, 0u};
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (uint64_t)gridDim.x * 256) {
+        const float p[3] = {x[i], y[i], z[i]};
+        perm[i] = (uint32_t)i;
+        // padding points (FLT_MAX) do not belong to the bounding box
+        if (!(p[0] == FLT_MAX && p[1] == FLT_MAX && p[2] == FLT_MAX)) {
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        uint32_t o = float_to_ordered(__float_as_uint(p[d]));
-        uint32_t lo = real ? o : 0xFFFFFFFFu, hi = real ? o : 0u;
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) {
-            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, s));
-            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, s));
-        }
-        if ((threadIdx.x & 31) == 0) {
-            if (lo != 0xFFFFFFFFu) atomicMin(&bounds6[d], lo);
-            if (hi != 0u) atomicMax(&bounds6[3 + d], hi);
+            for (int d = 0; d < 3; ++d) {
+                const uint32_t o = float_to_ordered(__float_as_uint(p[d]));
+                lo[d] = min(lo[d], o);
+                hi[d] = max(hi[d], o);
+            }
         }
     }
+    block_bounds(lo, hi, bounds6);
 }
 
 // key[i] = (segment(i) << 32) | orderable(coord[perm[i]]).  seg_prev/mid_prev describe the level
@@ -195,8 +214,130 @@ struct TreeArena {
     float *tiles; // n_padded / 8 tiles of 32 floats
 };
 
-// Orders the points held in (x0,y0,z0[,idx0]) into the arena and fills the node array.
-// perm must hold the identity on entry.
+// Select-and-partition build (tree_topdown.cuh + tree_bottom.cuh): orders the points held in
+// (x0,y0,z0[,idx0]) into the arena and fills the node array.  perm must hold the identity on entry;
+// the four columns are used as one of the two ping-pong buffers.  Everything is enqueued on `stream`
+// without host synchronisation except the final error check.
+inline void build_select(td::TopPlan const &plan, uint64_t n_padded, int leaf_size, int block_size,
+                         float *x0, float *y0, float *z0, uint32_t *perm, const uint32_t *idx0,
+                         const uint32_t *d_bounds6, TreeArena const &arena, cudaStream_t stream) {
+    using namespace td;
+    if (n_padded == 0) {
+        const nbk_node leaf{-1, 0.0f, 0u, 0u};
+        NBK_CUDA(cudaMemcpyAsync(arena.nodes, &leaf, sizeof leaf, cudaMemcpyHostToDevice, stream));
+        NBK_CUDA(cudaStreamSynchronize(stream));
+        return;
+    }
+    static const uint32_t nb = [] {
+        const char *v = std::getenv("NBK_BUILD_BINS");
+        uint32_t n = v ? (uint32_t)std::atoi(v) : 0u;
+        return (n >= 32 && n <= 2048 && (n & (n - 1)) == 0) ? n : 256u;
+    }();
+    const int T = plan.top_levels;
+    Scratch scratch(stream);
+    Seg *d_segs = scratch.get<Seg>(plan.segs.size());
+    uint32_t *d_lut = scratch.get<uint32_t>(plan.lut.size());
+    uint32_t *d_err = scratch.get<uint32_t>(1);
+    NBK_CUDA(cudaMemcpyAsync(d_segs, plan.segs.data(), plan.segs.size() * sizeof(Seg),
+                             cudaMemcpyHostToDevice, stream));
+    NBK_CUDA(cudaMemcpyAsync(d_lut, plan.lut.data(), plan.lut.size() * 4, cudaMemcpyHostToDevice, stream));
+    NBK_CUDA(cudaMemsetAsync(d_err, 0, 4, stream));
+    Columns cur{x0, y0, z0, perm}, alt{nullptr, nullptr, nullptr, nullptr};
+    if (T > 0) {
+        alt.x = scratch.get<float>(n_padded);
+        alt.y = scratch.get<float>(n_padded);
+        alt.z = scratch.get<float>(n_padded);
+        alt.id = scratch.get<uint32_t>(n_padded);
+        const uint64_t max_segs = (uint64_t)1 << (T - 1);
+        uint32_t *hist_cur = scratch.get<uint32_t>(max_segs * nb);
+        uint32_t *hist_alt = scratch.get<uint32_t>(max_segs * nb);
+        Sel *sel = scratch.get<Sel>(max_segs);
+        unsigned long long *pivot = scratch.get<unsigned long long>(max_segs);
+        uint32_t *cursors = scratch.get<uint32_t>(3 * max_segs);
+        float4 *bounds_cur = scratch.get<float4>(4 * max_segs);
+        float4 *bounds_alt = scratch.get<float4>(4 * max_segs);
+        unsigned long long *cand = scratch.get<unsigned long long>(n_padded);
+        NBK_CUDA(cudaMemsetAsync(hist_cur, 0, max_segs * nb * 4, stream));
+        NBK_CUDA(cudaMemsetAsync(hist_alt, 0, max_segs * nb * 4, stream));
+        init_bounds_kernel<<<1, 32, 0, stream>>>(d_bounds6, bounds_cur);
+        NBK_LAUNCHED();
+        const uint32_t chunks0 = (uint32_t)div_up(plan.biggest[0], kChunk);
+        hist_kernel<<<chunks0, kChunkThreads, nb * 4, stream>>>(cur.x, d_segs, bounds_cur, 0, chunks0, nb,
+                                                                hist_cur);
+        NBK_LAUNCHED();
+        for (int l = 0; l < T; ++l) {
+            const uint32_t nseg = 1u << l;
+            const Seg *segs_l = d_segs + (nseg - 1);
+            const Seg *segs_next = d_segs + (2 * nseg - 1);
+            const int dim = l % 3;
+            const uint32_t mc = (uint32_t)div_up(plan.biggest[l], kChunk);
+            const unsigned grid = nseg * mc;
+            const float *col = dim == 0 ? cur.x : (dim == 1 ? cur.y : cur.z);
+            if (plan.biggest[l] > kDirectMaxCount) {
+                // few huge segments: chunked candidate compaction, then one CTA per segment selects
+                bucket_kernel<<<(unsigned)div_up((uint64_t)nseg * 32, 256), 256, 0, stream>>>(
+                    segs_l, nseg, nb, hist_cur, sel, cursors);
+                NBK_LAUNCHED();
+                const uint32_t spans = (uint32_t)div_up(plan.biggest[l], kCompactSpan);
+                compact_kernel<<<nseg * spans, kCompactThreads, 0, stream>>>(
+                    col, cur.id, segs_l, bounds_cur, sel, dim, spans, nb, cursors, cand);
+                NBK_LAUNCHED();
+                select_kernel<false><<<nseg, 1024, 0, stream>>>(segs_l, sel, hist_cur, cursors, nb, col, cur.id,
+                                                                cand, dim, bounds_cur, bounds_alt, pivot,
+                                                                arena.nodes);
+                NBK_LAUNCHED();
+            } else {
+                // many moderate segments: the select CTA finds the bin and its candidates itself
+                select_kernel<true><<<nseg, kDirectThreads, 0, stream>>>(segs_l, sel, hist_cur, cursors, nb, col,
+                                                                         cur.id, cand, dim, bounds_cur,
+                                                                         bounds_alt, pivot, arena.nodes);
+                NBK_LAUNCHED();
+            }
+            if (l + 1 < T) {
+                partition_kernel<true><<<grid, kChunkThreads, 2 * nb * 4, stream>>>(
+                    cur, alt, segs_l, pivot, cursors, dim, mc, segs_next, bounds_cur, nb, hist_alt);
+            } else {
+                partition_kernel<false><<<grid, kChunkThreads, 0, stream>>>(
+                    cur, alt, segs_l, pivot, cursors, dim, mc, segs_next, bounds_cur, nb, hist_alt);
+            }
+            NBK_LAUNCHED();
+            std::swap(cur, alt);
+            std::swap(hist_cur, hist_alt);
+            std::swap(bounds_cur, bounds_alt);
+        }
+    }
+    BottomArgs args;
+    args.x = cur.x;
+    args.y = cur.y;
+    args.z = cur.z;
+    args.id = cur.id;
+    args.idx0 = idx0;
+    args.segs = d_segs + (((size_t)1 << T) - 1);
+    args.nseg = 1u << T;
+    args.level = T;
+    args.leaf = (uint32_t)std::max(leaf_size, 2 * block_size);
+    args.block = (uint32_t)block_size;
+    args.lut = d_lut;
+    args.nodes = arena.nodes;
+    args.tiles = arena.tiles;
+    args.error = d_err;
+    static const bool attr_set = [] {
+        NBK_CUDA(cudaFuncSetAttribute(bottom_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)kBottomSmem));
+        return true;
+    }();
+    (void)attr_set;
+    bottom_kernel<<<args.nseg, kBotThreads, kBottomSmem, stream>>>(args);
+    NBK_LAUNCHED();
+    uint32_t err = 0;
+    NBK_CUDA(cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, stream));
+    NBK_CUDA(cudaStreamSynchronize(stream)); // also keeps the plan's host tables alive long enough
+    if (err) throw Error(NBK_ERR_CUDA, "kd-tree build: sub-tree deeper than the bottom kernel's tables");
+}
+
+// Sort-based build (NBK_BUILD=sort; the first implementation, kept as the cross-check of the
+// select-and-partition build).  Orders the points held in (x0,y0,z0[,idx0]) into the arena and fills
+// the node array.  perm must hold the identity on entry.
 inline void build_levels(TopologyPlan const &plan, uint64_t n_padded, const float *x0,
                          const float *y0, const float *z0, const uint32_t *idx0, uint32_t *perm,
                          TreeArena const &arena, cudaStream_t stream) {

@@ -1,0 +1,166 @@
+#!/usr/bin/env python
+"""GPU check of the select-and-partition build against the compiled reference (test tooling).
+
+    python scripts/build_check.py [--big]        # prints one JSON line per case
+
+Per case: node arrays (dim/left/right AND split: the split is the rank-median coordinate, unique
+even under ties) equal to the reference's; idx is a permutation and tuples are preserved; every
+leaf holds the same point set as the reference's leaf wherever coordinates are unique; kNN parity
+on a query sample.  --big adds 2^24 points and times the 512^3 build.
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from nbodyhpc_b200 import capi  # noqa: E402
+from oracle import Oracle, Reference, compare_knn  # noqa: E402
+
+
+def leaf_ids(nodes, n):
+    out = np.full(n, -1, np.int64)
+    leaves = np.nonzero(nodes["dim"] == -1)[0]
+    for j in leaves:
+        out[nodes["left"][j]:nodes["right"][j]] = j
+    return out
+
+
+def check_case(name, pts, leaf, box=None, block=8, k=8, m=2000, seed=5):
+    n = len(pts)
+    t0 = time.perf_counter()
+    tree = capi.Tree.build(pts, leaf, box, block_size=block)
+    build_s = time.perf_counter() - t0
+    ref = Reference.Tree(pts, leaf, box) if (Reference.available() and block == 8) else None
+    res = {"case": name, "n": n, "leaf": leaf, "box": box, "block": block, "nodes": int(tree.size),
+           "build_ms_wall": round(1e3 * build_s, 2)}
+    nodes = tree.nodes()
+    x, y, z, idx = tree.points()
+    npad = tree.n
+    res["perm_ok"] = bool(np.array_equal(np.sort(idx), np.arange(npad, dtype=np.uint32)))
+    real = idx < n
+    res["tuples_ok"] = bool(np.array_equal(np.stack([x, y, z], 1)[real], pts[idx[real]]))
+    # topology against the host plan (counts only)
+    plan_nodes = capi.plan_topology(n, leaf, block)[0]
+    res["topology_ok"] = all(bool(np.array_equal(nodes[f], plan_nodes[f])) for f in ("dim", "left", "right"))
+    # the defining property of the reference's tree (kdtree_impl.hpp:108-125), valid under ties too:
+    # left child holds median_offset points, all <= split <= all of the right child, split = min(right)
+    coords = (x, y, z)
+    beg = np.zeros(len(nodes), np.int64)
+    end = np.zeros(len(nodes), np.int64)
+    inv_ok = True
+    for j in range(len(nodes) - 1, -1, -1):
+        nd = nodes[j]
+        if nd["dim"] == -1:
+            beg[j], end[j] = nd["left"], nd["right"]
+            continue
+        l, r = int(nd["left"]), int(nd["right"])
+        beg[j], end[j] = beg[l], end[r]
+        if len(nodes) > 40000 and j % 7:
+            continue  # sample the deep nodes of big trees
+        c = coords[nd["dim"]]
+        lmax = c[beg[l]:end[l]].max()
+        rmin = c[beg[r]:end[r]].min()
+        cnt = end[j] - beg[j]
+        if not (end[l] == beg[r] and end[l] - beg[l] == (cnt // 2 // block) * block and lmax <= nd["split"] == rmin):
+            inv_ok = False
+            res.setdefault("invariant_fail", []).append((j, int(nd["dim"]), float(lmax), float(nd["split"]), float(rmin)))
+            if len(res["invariant_fail"]) > 4:
+                break
+    res["invariant_ok"] = inv_ok
+    if ref is not None:
+        rn = ref.nodes()
+        res["size_ok"] = tree.size == ref.size and tree.n == ref.n
+        unique = all(len(np.unique(pts[:, a])) == n for a in range(3))
+        res["coords_unique"] = bool(unique)
+        # equal splits everywhere are guaranteed only without repeated coordinates (which of two equal
+        # coordinates goes left is unspecified in the reference, and changes the children's point sets)
+        same = bool(np.array_equal(nodes["split"].view(np.uint32), rn["split"].view(np.uint32)))
+        res["split_equal_ref" if unique else "split_equal_ref_info"] = same
+        if not same:
+            bad = np.nonzero(nodes["split"].view(np.uint32) != rn["split"].view(np.uint32))[0]
+            res["split_mismatch"] = [int(len(bad)), [(int(b), float(nodes["split"][b]), float(rn["split"][b])) for b in bad[:5]]]
+        if unique and n <= (1 << 22):
+            rx, ry, rz, ridx = ref.points()
+            mine = np.lexsort((idx, leaf_ids(nodes, npad)))
+            theirs = np.lexsort((ridx, leaf_ids(rn, npad)))
+            res["leaf_sets_equal_ref"] = bool(np.array_equal(idx[mine], ridx[theirs]))
+    rng = np.random.Generator(np.random.Philox(seed))
+    q = (rng.random((m, 3), dtype=np.float32) * np.float32(box or 1.0)).astype(np.float32)
+    d, i = tree.query(q, k)
+    checker = ref if ref is not None else Oracle.Tree(pts, leaf, box)
+    d_ref, i_ref = checker.query(q, k, workers=0)
+    rep = compare_knn(d, i, d_ref, i_ref, pts, q, box)
+    res["knn_ok"] = bool(rep.ok)
+    res["knn_rows_equal"] = int(rep.rows_equal)
+    bad = [key for key, v in res.items() if key.endswith("_ok") or key.endswith("_ref") if v is False]
+    res["PASS"] = not bad
+    print(json.dumps(res), flush=True)
+    return res["PASS"]
+
+
+def main():
+    big = "--big" in sys.argv
+    ok = True
+    rng = np.random.Generator(np.random.Philox(11))
+    for n, leaf in [(8, 64), (80, 32), (1000, 16), (8192, 16), (8192, 64), (8200, 64), (20000, 64), (100003, 64),
+                    (100003, 128), (300000, 16), (1 << 20, 64), (1 << 20, 1000), (3_000_001, 64), (200000, 20000),
+                    (70000, 9000)]:
+        ok &= check_case("uniform", Oracle.philox_points(n, 7), leaf)
+    ok &= check_case("uniform-periodic", Oracle.philox_points(500000, 42, 2.0), 64, box=2.0)
+    ok &= check_case("block16", Oracle.philox_points(100000, 3), 64, block=16)
+    ok &= check_case("block64", Oracle.philox_points(100000, 3), 100, block=64)
+    # heavy ties: a 64^3 lattice (each coordinate takes 64 values), and all points identical
+    g = (np.arange(64, dtype=np.float32) + 0.5) / 64
+    lat = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    ok &= check_case("lattice64", lat, 64, box=1.0)
+    ok &= check_case("lattice64-shuffled", lat[rng.permutation(len(lat))], 32)
+    ok &= check_case("identical", np.full((50000, 3), 0.25, np.float32), 64)
+    # clustered: a few tight Gaussian blobs + a uniform background, wide dynamic range
+    blobs = np.concatenate([rng.normal(c, s, (150000, 3)) for c, s in [(0.2, 1e-3), (0.7, 1e-2), (0.5, 1e-5)]]
+                           + [rng.random((50000, 3))]).astype(np.float32)
+    ok &= check_case("clustered", np.clip(blobs, 0, 1), 64, box=1.0)
+    ok &= check_case("negative-wide", ((rng.random((400000, 3)) - 0.5) * 2e6).astype(np.float32), 64)
+    if big:
+        ok &= check_case("uniform-2^24", rng.random((1 << 24, 3), dtype=np.float32), 64, box=1.0, m=20000)
+        import torch
+
+        for side in (256, 512):
+            n = side ** 3
+            pts = torch.rand((n, 3), device="cuda")
+            stream = torch.cuda.current_stream().cuda_stream
+            times = []
+            for it in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                t = capi.Tree.build_device(pts.data_ptr(), n, 64, 1.0, stream=stream)
+                e1.record()
+                torch.cuda.synchronize()
+                times.append(e0.elapsed_time(e1))
+                if it < 2:
+                    t.close()
+            print(json.dumps({"case": f"build {side}^3 uniform leaf 64", "ms": times,
+                              "mpts_per_s": n / (min(times) * 1e-3) / 1e6}), flush=True)
+            # sampled exhaustive check of the last tree
+            q = torch.rand((256, 3), device="cuda")
+            d = torch.empty((256, 8), device="cuda")
+            i = torch.empty((256, 8), device="cuda", dtype=torch.int32)
+            t.query_device(q.data_ptr(), 256, 8, d.data_ptr(), i.data_ptr(), stream)
+            torch.cuda.synchronize()
+            dd = pts[None, :, :] - q[:4, None, :]
+            dd = torch.minimum(dd * dd, torch.minimum((dd - 1) ** 2, (dd + 1) ** 2)).sum(-1)
+            best = torch.topk(dd, 8, largest=False).values.sqrt()
+            err = float((best - d[:4]).abs().max())
+            print(json.dumps({"case": f"exhaustive sample {side}^3", "max_abs_err": err}), flush=True)
+            ok &= err < 1e-6
+            t.close()
+            del pts
+    print("ALL PASS" if ok else "FAILURES", flush=True)
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
