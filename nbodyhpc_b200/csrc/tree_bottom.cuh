@@ -3,16 +3,22 @@
 //
 // The reference recurses: select the rank-median element along dim, split, recurse with the next
 // dim (kdtree_impl.hpp:98-157).  Here the three coordinate orders of the segment are established
-// ONCE (three stable LSD radix sorts of (orderable coordinate, local id) in shared memory); after
-// that a level of the recursion is a single ranking pass: walking the order of that level's
-// dimension, every element counts the elements of its own sub-segment that precede it, which is its
-// rank inside the sub-segment -- rank < median_offset goes left, the element of rank ==
-// median_offset supplies the split (kdtree_impl.hpp:108-125).  No element moves until the end, when
-// every point is written once into its final 128-byte tile.
+// ONCE, as three lists of local element ids sorted by (orderable coordinate, id).  A level of the
+// recursion then moves no point data at all:
+//   * every sub-segment is the SAME position range [beg, beg+cnt) in all three lists;
+//   * in the list of the level's split dimension the rank-median element simply sits at position
+//     beg + median_offset: it supplies the split (kdtree_impl.hpp:108-125) and everything from there
+//     on is the right child;
+//   * the other two lists are stably partitioned inside every range by that left/right flag (one
+//     block-wide prefix sum per level), which keeps them sorted inside both children.
+// At the end the x-list is the final leaf order; every point is read once more and written once into
+// its 128-byte tile.
 //
-// Ties between equal coordinates are broken by id (the sorts are stable and start from id order), the
-// same total order the top phase uses, so the result does not depend on the order in which the top
-// phase happened to write the segment.
+// Sorting: one counting pass over 4096 value-range bins (shared-memory atomics) plus an exact
+// (coordinate, id) ranking inside each bin.  Degenerate distributions (a bin with more than kRunMax
+// elements: heavy ties, extreme clustering) take a stable LSD radix sort started from id order
+// instead.  Either way the order is the total order (coordinate, id) that the top phase uses, so the
+// result does not depend on the order in which the top phase happened to write the segment.
 #pragma once
 
 #include "tree_topdown.cuh"
@@ -22,37 +28,36 @@ namespace td {
 
 constexpr int kBotThreads = 1024;
 constexpr int kBotWarps = kBotThreads / 32;
-constexpr int kBotItems = kBottomCap / kBotThreads; // 8
+constexpr int kBotItems = kBottomCap / kBotThreads; // 8 = one tile / one block_size unit per thread
 constexpr int kBotMaxIds = 1024;                    // heap ids of sub-segments: 10 levels
 constexpr uint16_t kNoSplit16 = 0xFFFFu;
+constexpr uint32_t kSortBins = 4096;
+constexpr uint32_t kRunMax = 64;
+static_assert(kBotItems == 8, "a thread owns 8 consecutive list positions (one tile)");
 
 // shared-memory carve-up (bytes)
-constexpr size_t kOffKeyA = 0;                                  // u32[8192]
-constexpr size_t kOffKeyB = kOffKeyA + 4 * kBottomCap;          // u32[8192]
-constexpr size_t kOffLidA = kOffKeyB + 4 * kBottomCap;          // u16[8192]
-constexpr size_t kOffLidB = kOffLidA + 2 * kBottomCap;          // u16[8192]
-constexpr size_t kOffList = kOffLidB + 2 * kBottomCap;          // u16[3][8192]
-constexpr size_t kOffIdOrd = kOffList + 3 * 2 * kBottomCap;     // u16[8192]
-constexpr size_t kOffSubseg = kOffIdOrd + 2 * kBottomCap;       // u16[8192]
-constexpr size_t kOffWhist = kOffSubseg + 2 * kBottomCap;       // u16[32][256] (sort passes)
-constexpr size_t kOffTabCnt = kOffWhist + 2 * kBotWarps * 256;  // u16[1024]
-constexpr size_t kOffTabBeg = kOffTabCnt + 2 * kBotMaxIds;      // u16[1024]
-constexpr size_t kOffTabMed = kOffTabBeg + 2 * kBotMaxIds;      // u16[1024]
-constexpr size_t kOffTabNode = kOffTabMed + 2 * kBotMaxIds;     // u32[1024]
-constexpr size_t kOffDstart = kOffTabNode + 4 * kBotMaxIds;     // u32[256]
-constexpr size_t kOffMisc = kOffDstart + 4 * 256;               // u32[8]
-constexpr size_t kBottomSmem = kOffMisc + 4 * 8;
-// aliases: ranking histogram u16[32][512] over keyA (dead after the sorts); staging tiles
-// (16 B x 8192 = 128 KB) over [0, kOffList + 2*2*kBottomCap) = keyA..list[1]; final positions over list[2]
-static_assert(kOffList + 2 * 2 * kBottomCap >= 16 * (size_t)kBottomCap, "staging area too small");
+constexpr size_t kOffList = 0;                                   // u16[2][3][8192]  lists [buffer][dim]
+constexpr size_t kOffTmpKey = kOffList + 6 * 2 * kBottomCap;     // u32[8192]        sort scratch
+constexpr size_t kOffTmpLid = kOffTmpKey + 4 * kBottomCap;       // u16[8192]
+constexpr size_t kOffHist = kOffTmpLid + 2 * kBottomCap;         // u32[4097]        (radix: u16[32][256])
+constexpr size_t kOffSegPos = kOffHist + 4 * (kSortBins + 4);    // u16[8192]        sub-segment of a position
+constexpr size_t kOffSide = kOffSegPos + 2 * kBottomCap;         // u8[8192]         1 = right child
+constexpr size_t kOffTabCnt = kOffSide + kBottomCap;             // u16[1024]
+constexpr size_t kOffTabBeg = kOffTabCnt + 2 * kBotMaxIds;       // u16[1024]
+constexpr size_t kOffTabMed = kOffTabBeg + 2 * kBotMaxIds;       // u16[1024]
+constexpr size_t kOffTabNode = kOffTabMed + 2 * kBotMaxIds;      // u32[1024]
+constexpr size_t kOffThreadP = kOffTabNode + 4 * kBotMaxIds;     // u32[1024]        packed prefix per thread
+constexpr size_t kOffDstart = kOffThreadP + 4 * kBotThreads;     // u32[256]
+constexpr size_t kOffMisc = kOffDstart + 4 * 256;                // u32[80]
+constexpr size_t kBottomSmem = kOffMisc + 4 * 80;
+// radix fallback aliases: keyA = tmpKey, lidA = tmpLid, whist = hist; keyB over the second buffers of
+// the x and y lists (contiguous 32 KB), lidB over the second buffer of the z list, idord over segpos:
+// all unused while sorting
 static_assert(kBottomSmem <= 227 * 1024, "bottom kernel shared memory");
 
-// Block-wide stable rank of every element inside its digit class.  Elements are laid out
-// warp-blocked: warp w owns positions [w*256, w*256+256), round r covers w*256 + r*32 + lane.
-// whist: u16[kBotWarps][nslots].  Returns rank[r] = number of elements with the same digit at
-// smaller positions.  If `totals` is not null, totals[d] = size of class d.
-// Lanes of the warp holding the same digit (nbits wide).  One ballot per bit: the MATCH.ANY
-// instruction serialises over the distinct values of a warp and is several times slower here.
+// ---- radix fallback (stable, 8 bits per pass) ----------------------------------------------------------
+// Lanes of the warp holding the same digit.  One ballot per bit: the MATCH.ANY instruction
+// serialises over the distinct values of a warp and is several times slower here.
 __device__ __forceinline__ unsigned match_digit(uint32_t d, bool ok, int nbits) {
     unsigned peers = __ballot_sync(0xffffffffu, ok);
     for (int b = 0; b < nbits; ++b) {
@@ -63,21 +68,24 @@ __device__ __forceinline__ unsigned match_digit(uint32_t d, bool ok, int nbits) 
     return peers;
 }
 
+// Block-wide stable rank of every element inside its digit class.  Elements are laid out
+// warp-blocked: warp w owns positions [w*256, w*256+256), round r covers w*256 + r*32 + lane.
+// whist: u16[kBotWarps][256].  rank[r] = number of elements with the same digit at smaller
+// positions; totals[d] = size of class d.
 __device__ __forceinline__ void block_rank(const uint32_t (&digit)[kBotItems], const bool (&ok)[kBotItems],
-                                           uint32_t nslots, int nbits, uint16_t *whist, uint32_t *totals,
-                                           uint32_t (&rank)[kBotItems]) {
+                                           uint16_t *whist, uint32_t *totals, uint32_t (&rank)[kBotItems]) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt = (1u << lane) - 1u;
     {
         uint32_t *w32 = reinterpret_cast<uint32_t *>(whist);
-        for (uint32_t i = tid; i < nslots * kBotWarps / 2; i += kBotThreads) w32[i] = 0u;
+        for (uint32_t i = tid; i < 256u * kBotWarps / 2; i += kBotThreads) w32[i] = 0u;
     }
     __syncthreads();
-    uint16_t *wh = whist + (uint32_t)warp * nslots;
+    uint16_t *wh = whist + (uint32_t)warp * 256u;
 #pragma unroll
     for (int r = 0; r < kBotItems; ++r) {
         const uint32_t d = ok[r] ? digit[r] : 0u;
-        const unsigned peers = match_digit(d, ok[r], nbits);
+        const unsigned peers = match_digit(d, ok[r], 8);
         const uint32_t pre = ok[r] ? wh[d] : 0u;
         __syncwarp();
         if (ok[r] && (peers & lt) == 0u) wh[d] = (uint16_t)(pre + __popc(peers));
@@ -85,15 +93,15 @@ __device__ __forceinline__ void block_rank(const uint32_t (&digit)[kBotItems], c
         rank[r] = pre + __popc(peers & lt);
     }
     __syncthreads();
-    for (uint32_t d = tid; d < nslots; d += kBotThreads) {
+    for (uint32_t d = tid; d < 256u; d += kBotThreads) {
         uint32_t run = 0;
 #pragma unroll 8
         for (int w = 0; w < kBotWarps; ++w) {
-            const uint32_t t = whist[(uint32_t)w * nslots + d];
-            whist[(uint32_t)w * nslots + d] = (uint16_t)run;
+            const uint32_t t = whist[(uint32_t)w * 256u + d];
+            whist[(uint32_t)w * 256u + d] = (uint16_t)run;
             run += t;
         }
-        if (totals) totals[d] = run;
+        totals[d] = run;
     }
     __syncthreads();
 #pragma unroll
@@ -103,11 +111,10 @@ __device__ __forceinline__ void block_rank(const uint32_t (&digit)[kBotItems], c
 
 // Stable LSD radix sort of (key, lid) pairs, n <= 8192, input in (keyA, lidA); the sorted lids go to
 // `out`.  Byte positions on which all keys agree are skipped.
-__device__ __forceinline__ void block_sort(uint32_t *keyA, uint32_t *keyB, uint16_t *lidA, uint16_t *lidB,
-                                           uint32_t n, uint16_t *whist, uint32_t *dstart, uint32_t *misc,
-                                           uint16_t *out) {
+__device__ __noinline__ void block_sort(uint32_t *keyA, uint32_t *keyB, uint16_t *lidA, uint16_t *lidB,
+                                        uint32_t n, uint16_t *whist, uint32_t *dstart, uint32_t *misc,
+                                        uint16_t *out) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // which key bits vary at all
     if (tid == 0) misc[0] = 0u;
     __syncthreads();
     {
@@ -134,9 +141,8 @@ __device__ __forceinline__ void block_sort(uint32_t *keyA, uint32_t *keyB, uint1
             l[r] = ok[r] ? lin[i] : (uint16_t)0;
             digit[r] = (k[r] >> shift) & 0xFFu;
         }
-        block_rank(digit, ok, 256u, 8, whist, dstart, rank);
-        // exclusive scan of the 256 class sizes (warp 0, 8 per lane)
-        if (warp == 0) {
+        block_rank(digit, ok, whist, dstart, rank);
+        if (warp == 0) { // exclusive scan of the 256 class sizes, 8 per lane
             uint32_t a[8], sum = 0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -171,6 +177,30 @@ __device__ __forceinline__ void block_sort(uint32_t *keyA, uint32_t *keyB, uint1
     }
     for (uint32_t i = tid; i < n; i += kBotThreads) out[i] = lin[i];
     __syncthreads();
+}
+
+// Block-wide exclusive prefix sum of one uint32 per thread (1024 threads); wsum: u32[32] scratch.
+__device__ __forceinline__ uint32_t block_exclusive_sum(uint32_t v, uint32_t *wsum, uint32_t &total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    const uint32_t w = wsum[lane];
+    uint32_t winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += t;
+    }
+    total = __shfl_sync(0xffffffffu, winc, 31);
+    const uint32_t wofs = __shfl_sync(0xffffffffu, winc - w, warp);
+    __syncthreads();
+    return wofs + incl - v;
 }
 
 struct BottomArgs {
@@ -222,41 +252,134 @@ __global__ void __launch_bounds__(kBotThreads, 1) bottom_kernel(BottomArgs a) {
         return;
     }
 
-    uint32_t *keyA = reinterpret_cast<uint32_t *>(smem + kOffKeyA);
-    uint32_t *keyB = reinterpret_cast<uint32_t *>(smem + kOffKeyB);
-    uint16_t *lidA = reinterpret_cast<uint16_t *>(smem + kOffLidA);
-    uint16_t *lidB = reinterpret_cast<uint16_t *>(smem + kOffLidB);
-    uint16_t *list = reinterpret_cast<uint16_t *>(smem + kOffList);
-    uint16_t *idord = reinterpret_cast<uint16_t *>(smem + kOffIdOrd);
-    uint16_t *subseg = reinterpret_cast<uint16_t *>(smem + kOffSubseg);
-    uint16_t *whist = reinterpret_cast<uint16_t *>(smem + kOffWhist);
+    uint16_t *lists = reinterpret_cast<uint16_t *>(smem + kOffList); // [buf][dim][8192]
+    uint32_t *tmp_key = reinterpret_cast<uint32_t *>(smem + kOffTmpKey);
+    uint16_t *tmp_lid = reinterpret_cast<uint16_t *>(smem + kOffTmpLid);
+    uint32_t *hist = reinterpret_cast<uint32_t *>(smem + kOffHist);
+    uint16_t *seg_of_pos = reinterpret_cast<uint16_t *>(smem + kOffSegPos);
+    uint8_t *side = reinterpret_cast<uint8_t *>(smem + kOffSide);
     uint16_t *t_cnt = reinterpret_cast<uint16_t *>(smem + kOffTabCnt);
     uint16_t *t_beg = reinterpret_cast<uint16_t *>(smem + kOffTabBeg);
     uint16_t *t_med = reinterpret_cast<uint16_t *>(smem + kOffTabMed);
     uint32_t *t_node = reinterpret_cast<uint32_t *>(smem + kOffTabNode);
+    uint32_t *thread_p = reinterpret_cast<uint32_t *>(smem + kOffThreadP);
     uint32_t *dstart = reinterpret_cast<uint32_t *>(smem + kOffDstart);
     uint32_t *misc = reinterpret_cast<uint32_t *>(smem + kOffMisc);
-    uint16_t *rhist = reinterpret_cast<uint16_t *>(smem + kOffKeyA); // ranking passes (keys are dead)
-    float *stage = reinterpret_cast<float *>(smem);
-    uint16_t *pos_of = list + 2 * kBottomCap;                         // over list[2]
+    auto list_of = [&](int d, int buf) { return lists + ((size_t)buf * 3 + d) * kBottomCap; };
 
-    // ---- id order, then the three coordinate orders -------------------------------------------------
-    for (uint32_t i = tid; i < n; i += kBotThreads) {
-        keyA[i] = a.id[gbase + i];
-        lidA[i] = (uint16_t)i;
-    }
-    __syncthreads();
-    block_sort(keyA, keyB, lidA, lidB, n, whist, dstart, misc, idord);
+    // ---- the three coordinate orders --------------------------------------------------------------------
+    bool have_idord = false;
+    uint16_t *idord = seg_of_pos; // radix fallback only
 #pragma unroll 1
     for (int d = 0; d < 3; ++d) {
         const float *col = d == 0 ? a.x : (d == 1 ? a.y : a.z);
-        for (uint32_t i = tid; i < n; i += kBotThreads) {
-            const uint16_t e = idord[i];
-            keyA[i] = float_to_ordered(__float_as_uint(col[gbase + e]));
-            lidA[i] = e;
+        uint16_t *out = list_of(d, 0);
+        float v[kBotItems];
+        uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
+#pragma unroll
+        for (int r = 0; r < kBotItems; ++r) {
+            const uint32_t e = r * kBotThreads + tid;
+            v[r] = e < n ? col[gbase + e] : 0.0f;
+            if (e < n) {
+                const uint32_t key = float_to_ordered(__float_as_uint(v[r]));
+                kmin = min(kmin, key);
+                kmax = max(kmax, key);
+            }
+        }
+        kmin = __reduce_min_sync(0xffffffffu, kmin);
+        kmax = __reduce_max_sync(0xffffffffu, kmax);
+        if (lane == 0) {
+            misc[8 + warp] = kmin;
+            misc[40 + warp] = kmax;
+        }
+        for (uint32_t b = tid; b < kSortBins + 1; b += kBotThreads) hist[b] = 0u;
+        __syncthreads();
+        kmin = __reduce_min_sync(0xffffffffu, misc[8 + lane]);
+        kmax = __reduce_max_sync(0xffffffffu, misc[40 + lane]);
+        const float lo = __uint_as_float(ordered_to_float(kmin)), hi = __uint_as_float(ordered_to_float(kmax));
+        const float scale = bin_scale(lo, hi, kSortBins);
+        uint32_t bin[kBotItems], lr[kBotItems];
+#pragma unroll
+        for (int r = 0; r < kBotItems; ++r) {
+            const uint32_t e = r * kBotThreads + tid;
+            bin[r] = bin_of(v[r], lo, scale, kSortBins);
+            lr[r] = e < n ? atomicAdd(&hist[bin[r]], 1u) : 0u;
         }
         __syncthreads();
-        block_sort(keyA, keyB, lidA, lidB, n, whist, dstart, misc, list + d * kBottomCap);
+        // exclusive scan of the bin counts (4 per thread) -> bin starts; hist[kSortBins] = n
+        bool long_run = false;
+        {
+            uint32_t c[4], sum = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                c[i] = hist[tid * 4 + i];
+                sum += c[i];
+                long_run = long_run || c[i] > kRunMax;
+            }
+            uint32_t total;
+            uint32_t run = block_exclusive_sum(sum, misc + 8, total);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                hist[tid * 4 + i] = run;
+                run += c[i];
+            }
+            if (tid == 0) hist[kSortBins] = n;
+        }
+        if (__syncthreads_or(long_run ? 1 : 0)) {
+            // degenerate distribution: stable radix sort by coordinate, starting from id order
+            uint32_t *keyA = tmp_key, *keyB = reinterpret_cast<uint32_t *>(list_of(0, 1)); // x+y second buffers
+            uint16_t *lidA = tmp_lid, *lidB = list_of(2, 1);
+            uint16_t *whist = reinterpret_cast<uint16_t *>(hist);
+            if (!have_idord) {
+                for (uint32_t i = tid; i < n; i += kBotThreads) {
+                    keyA[i] = a.id[gbase + i];
+                    lidA[i] = (uint16_t)i;
+                }
+                __syncthreads();
+                block_sort(keyA, keyB, lidA, lidB, n, whist, dstart, misc, idord);
+                have_idord = true;
+            }
+            for (uint32_t i = tid; i < n; i += kBotThreads) {
+                const uint16_t e = idord[i];
+                keyA[i] = float_to_ordered(__float_as_uint(col[gbase + e]));
+                lidA[i] = e;
+            }
+            __syncthreads();
+            block_sort(keyA, keyB, lidA, lidB, n, whist, dstart, misc, out);
+            continue;
+        }
+        // scatter by bin (arrival order inside a bin), then rank exactly inside each bin
+#pragma unroll
+        for (int r = 0; r < kBotItems; ++r) {
+            const uint32_t e = r * kBotThreads + tid;
+            if (e < n) {
+                const uint32_t pos = hist[bin[r]] + lr[r];
+                tmp_key[pos] = float_to_ordered(__float_as_uint(v[r]));
+                tmp_lid[pos] = (uint16_t)e;
+            }
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int r = 0; r < kBotItems; ++r) {
+            const uint32_t p = r * kBotThreads + tid;
+            if (p < n) {
+                const uint32_t key = tmp_key[p];
+                const uint16_t lid = tmp_lid[p];
+                const uint32_t b = bin_of(__uint_as_float(ordered_to_float(key)), lo, scale, kSortBins);
+                const uint32_t s0 = hist[b], s1 = hist[b + 1];
+                uint32_t rank = 0;
+                for (uint32_t q = s0; q < s1; ++q) {
+                    const uint32_t kq = tmp_key[q];
+                    if (kq < key) {
+                        ++rank;
+                    } else if (kq == key && q != p) {
+                        if (a.id[gbase + tmp_lid[q]] < a.id[gbase + lid]) ++rank; // equal coordinates: by id
+                    }
+                }
+                out[s0 + rank] = lid;
+            }
+        }
+        __syncthreads();
     }
 
     // ---- root of the sub-tree ------------------------------------------------------------------------
@@ -272,41 +395,105 @@ __global__ void __launch_bounds__(kBotThreads, 1) bottom_kernel(BottomArgs a) {
         nd->left = sg.node + 1;
         nd->right = sg.node + 1 + a.lut[med >> 3];
     }
-    for (uint32_t i = tid; i < n; i += kBotThreads) subseg[i] = 1;
+    for (uint32_t i = tid; i < n; i += kBotThreads) seg_of_pos[i] = 1;
     __syncthreads();
 
-    // ---- one ranking pass per level -------------------------------------------------------------------
+    // ---- levels ------------------------------------------------------------------------------------------
+    // Thread t owns list positions [8t, 8t+8): sub-segment boundaries and medians are multiples of
+    // block_size (a multiple of 8), so the 8 positions always lie in one sub-segment and on one side.
+    const uint32_t p0 = (uint32_t)tid * 8u;
+    const bool mine = p0 < n;
+    int cur0 = 0, cur1 = 0, cur2 = 0; // which buffer holds the current x / y / z list
     int j = 0;
     while (true) {
         const int dim = (a.level + j) % 3;
-        const float *col = dim == 0 ? a.x : (dim == 1 ? a.y : a.z);
-        const uint16_t *order = list + dim * kBottomCap;
+        const int d1 = dim == 2 ? 0 : dim + 1, d2 = d1 == 2 ? 0 : d1 + 1;
+        const int cdim = dim == 0 ? cur0 : (dim == 1 ? cur1 : cur2);
+        const int c1 = d1 == 0 ? cur0 : (d1 == 1 ? cur1 : cur2);
+        const int c2 = d2 == 0 ? cur0 : (d2 == 1 ? cur1 : cur2);
         const uint32_t first = 1u << j; // heap ids of this level: [first, 2*first)
-        uint32_t digit[kBotItems], rank[kBotItems];
-        uint16_t e[kBotItems];
-        bool ok[kBotItems];
+        // A: side of every element from the split dimension's list; split value; new sub-segment ids
+        if (mine) {
+            const uint32_t h = seg_of_pos[p0];
+            const uint32_t med = t_med[h];
+            uint32_t nh = 2u * h;
+            if (med != kNoSplit16) {
+                const uint32_t rel = p0 - t_beg[h];
+                const bool right = rel >= med;
+                const uint4 pk = *reinterpret_cast<const uint4 *>(list_of(dim, cdim) + p0);
+                const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+                const uint8_t flag = right ? 1 : 0;
 #pragma unroll
-        for (int r = 0; r < kBotItems; ++r) {
-            const uint32_t i = (uint32_t)warp * 256u + r * 32u + lane;
-            ok[r] = i < n;
-            e[r] = ok[r] ? order[i] : (uint16_t)0;
-            digit[r] = ok[r] ? (uint32_t)subseg[e[r]] - first : 0u;
-        }
-        block_rank(digit, ok, first, j, rhist, nullptr, rank);
-#pragma unroll
-        for (int r = 0; r < kBotItems; ++r) {
-            if (ok[r]) {
-                const uint32_t h = digit[r] + first;
-                const uint32_t med = t_med[h];
-                uint32_t nh = 2u * h;
-                if (med != kNoSplit16) {
-                    if (rank[r] >= med) nh += 1u;
-                    if (rank[r] == med) a.nodes[t_node[h]].split = col[gbase + e[r]];
+                for (int i = 0; i < 4; ++i) {
+                    side[w[i] & 0xFFFFu] = flag;
+                    side[w[i] >> 16] = flag;
                 }
-                subseg[e[r]] = (uint16_t)nh;
+                if (rel == med) {
+                    const float *col = dim == 0 ? a.x : (dim == 1 ? a.y : a.z);
+                    a.nodes[t_node[h]].split = col[gbase + (w[0] & 0xFFFFu)]; // kdtree_impl.hpp:116-125
+                }
+                if (right) nh += 1u;
             }
+            const uint32_t two = nh | (nh << 16);
+            *reinterpret_cast<uint4 *>(seg_of_pos + p0) = make_uint4(two, two, two, two);
         }
-        // tables of level j+1
+        __syncthreads();
+        // B: stable partition of the other two lists inside every splitting sub-segment
+        {
+            uint32_t e1[4] = {0, 0, 0, 0}, e2[4] = {0, 0, 0, 0};
+            uint32_t left1 = 0, left2 = 0; // bit i: element i goes left
+            uint32_t med = kNoSplit16, beg = 0;
+            if (mine) {
+                const uint32_t h = seg_of_pos[p0] >> 1;
+                med = t_med[h];
+                beg = t_beg[h];
+                const uint4 a1 = *reinterpret_cast<const uint4 *>(list_of(d1, c1) + p0);
+                const uint4 a2 = *reinterpret_cast<const uint4 *>(list_of(d2, c2) + p0);
+                e1[0] = a1.x; e1[1] = a1.y; e1[2] = a1.z; e1[3] = a1.w;
+                e2[0] = a2.x; e2[1] = a2.y; e2[2] = a2.z; e2[3] = a2.w;
+                if (med != kNoSplit16) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        left1 |= (side[e1[i] & 0xFFFFu] ? 0u : 1u) << (2 * i);
+                        left1 |= (side[e1[i] >> 16] ? 0u : 1u) << (2 * i + 1);
+                        left2 |= (side[e2[i] & 0xFFFFu] ? 0u : 1u) << (2 * i);
+                        left2 |= (side[e2[i] >> 16] ? 0u : 1u) << (2 * i + 1);
+                    }
+                }
+            }
+            uint32_t total;
+            const uint32_t packed = __popc(left1) | (__popc(left2) << 16); // both prefix sums at once (<= 8192)
+            const uint32_t myp = block_exclusive_sum(packed, misc + 8, total);
+            thread_p[tid] = myp;
+            __syncthreads();
+            if (mine) {
+                uint16_t *o1 = list_of(d1, c1 ^ 1), *o2 = list_of(d2, c2 ^ 1);
+                if (med != kNoSplit16) {
+                    const uint32_t at_beg = thread_p[beg >> 3];
+                    uint32_t l1 = (myp & 0xFFFFu) - (at_beg & 0xFFFFu); // lefts of this sub-segment before p0
+                    uint32_t l2 = (myp >> 16) - (at_beg >> 16);
+                    const uint32_t rel = p0 - beg;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const uint32_t v1 = (i & 1) ? (e1[i >> 1] >> 16) : (e1[i >> 1] & 0xFFFFu);
+                        const uint32_t v2 = (i & 1) ? (e2[i >> 1] >> 16) : (e2[i >> 1] & 0xFFFFu);
+                        const bool g1 = (left1 >> i) & 1u, g2 = (left2 >> i) & 1u;
+                        const uint32_t q1 = g1 ? beg + l1 : beg + med + (rel + i - l1);
+                        const uint32_t q2 = g2 ? beg + l2 : beg + med + (rel + i - l2);
+                        o1[q1] = (uint16_t)v1;
+                        o2[q2] = (uint16_t)v2;
+                        l1 += g1 ? 1u : 0u;
+                        l2 += g2 ? 1u : 0u;
+                    }
+                } else {
+                    *reinterpret_cast<uint4 *>(o1 + p0) = make_uint4(e1[0], e1[1], e1[2], e1[3]);
+                    *reinterpret_cast<uint4 *>(o2 + p0) = make_uint4(e2[0], e2[1], e2[2], e2[3]);
+                }
+            }
+            if (d1 == 0) cur0 ^= 1; else if (d1 == 1) cur1 ^= 1; else cur2 ^= 1;
+            if (d2 == 0) cur0 ^= 1; else if (d2 == 1) cur1 ^= 1; else cur2 ^= 1;
+        }
+        // C: tables of level j+1
         bool splits_more = false;
         if (2u * first < (uint32_t)kBotMaxIds) {
             const int ndim = (a.level + j + 1) % 3;
@@ -365,48 +552,36 @@ __global__ void __launch_bounds__(kBotThreads, 1) bottom_kernel(BottomArgs a) {
         if (!__syncthreads_or(splits_more ? 1 : 0)) break;
     }
 
-    // ---- final position inside the leaf: rank in id order among the leaf's points ------------------------
-    {
-        const uint32_t first = 1u << j;
-        const bool have_tables = first < (uint32_t)kBotMaxIds;
-        uint32_t digit[kBotItems], rank[kBotItems];
-        uint16_t e[kBotItems];
-        bool ok[kBotItems];
+    // ---- the x-list is the final order: one 128-byte tile per thread ------------------------------------------
+    if (mine) {
+        const uint4 pk = *reinterpret_cast<const uint4 *>(list_of(0, cur0) + p0);
+        const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+        float tx[8], ty[8], tz[8];
+        uint32_t ti[8];
 #pragma unroll
-        for (int r = 0; r < kBotItems; ++r) {
-            const uint32_t i = (uint32_t)warp * 256u + r * 32u + lane;
-            ok[r] = have_tables && i < n;
-            e[r] = ok[r] ? idord[i] : (uint16_t)0;
-            digit[r] = ok[r] ? (uint32_t)subseg[e[r]] - first : 0u;
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t e = (i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xFFFFu);
+            tx[i] = a.x[gbase + e];
+            ty[i] = a.y[gbase + e];
+            tz[i] = a.z[gbase + e];
+            ti[i] = a.id[gbase + e];
         }
-        block_rank(digit, ok, have_tables ? first : 1u, have_tables ? j : 0, rhist, nullptr, rank);
+        if (a.idx0) {
 #pragma unroll
-        for (int r = 0; r < kBotItems; ++r)
-            if (ok[r]) pos_of[e[r]] = (uint16_t)(t_beg[digit[r] + first] + rank[r]);
-        __syncthreads();
-    }
-    // ---- stage the tiles in shared memory, then one contiguous copy ---------------------------------------
-    const bool have_positions = (1u << j) < (uint32_t)kBotMaxIds; // false only after *a.error was set
-    uint32_t my_pos[kBotItems];
-#pragma unroll
-    for (int r = 0; r < kBotItems; ++r) {
-        const uint32_t i = r * kBotThreads + tid;
-        my_pos[r] = i < n ? (have_positions ? (uint32_t)pos_of[i] : i) : 0u;
-    }
-    __syncthreads(); // pos_of (list[2]) is outside the staging area, rhist (keyA) is inside: all reads done
-#pragma unroll
-    for (int r = 0; r < kBotItems; ++r) {
-        const uint32_t i = r * kBotThreads + tid;
-        if (i < n) {
-            const uint32_t id = a.id[gbase + i];
-            put_tile(stage, my_pos[r], a.x[gbase + i], a.y[gbase + i], a.z[gbase + i],
-                     a.idx0 ? a.idx0[id] : id);
+            for (int i = 0; i < 8; ++i) ti[i] = a.idx0[ti[i]];
         }
+        float4 *dst = reinterpret_cast<float4 *>(a.tiles + ((gbase + p0) >> 3) * 32);
+        dst[0] = make_float4(tx[0], tx[1], tx[2], tx[3]);
+        dst[1] = make_float4(tx[4], tx[5], tx[6], tx[7]);
+        dst[2] = make_float4(ty[0], ty[1], ty[2], ty[3]);
+        dst[3] = make_float4(ty[4], ty[5], ty[6], ty[7]);
+        dst[4] = make_float4(tz[0], tz[1], tz[2], tz[3]);
+        dst[5] = make_float4(tz[4], tz[5], tz[6], tz[7]);
+        dst[6] = make_float4(__uint_as_float(ti[0]), __uint_as_float(ti[1]), __uint_as_float(ti[2]),
+                             __uint_as_float(ti[3]));
+        dst[7] = make_float4(__uint_as_float(ti[4]), __uint_as_float(ti[5]), __uint_as_float(ti[6]),
+                             __uint_as_float(ti[7]));
     }
-    __syncthreads();
-    float4 *dst = reinterpret_cast<float4 *>(a.tiles + (gbase >> 3) * 32);
-    const float4 *src = reinterpret_cast<const float4 *>(stage);
-    for (uint32_t i = tid; i < n; i += kBotThreads) dst[i] = src[i]; // n points = n float4
 }
 
 } // namespace td
