@@ -14,7 +14,7 @@
 // At the end the x-list is the final leaf order; every point is read once more and written once into
 // its 128-byte tile.
 //
-// Sorting: one counting pass over 4096 value-range bins (shared-memory atomics) plus an exact
+// Sorting: one counting pass over 8192 value-range bins (shared-memory atomics) plus an exact
 // (coordinate, id) ranking inside each bin.  Degenerate distributions (a bin with more than kRunMax
 // elements: heavy ties, extreme clustering) take a stable LSD radix sort started from id order
 // instead.  Either way the order is the total order (coordinate, id) that the top phase uses, so the
@@ -31,7 +31,7 @@ constexpr int kBotWarps = kBotThreads / 32;
 constexpr int kBotItems = kBottomCap / kBotThreads; // 8 = one tile / one block_size unit per thread
 constexpr int kBotMaxIds = 1024;                    // heap ids of sub-segments: 10 levels
 constexpr uint16_t kNoSplit16 = 0xFFFFu;
-constexpr uint32_t kSortBins = 4096;
+constexpr uint32_t kSortBins = 8192;
 constexpr uint32_t kRunMax = 64;
 static_assert(kBotItems == 8, "a thread owns 8 consecutive list positions (one tile)");
 
@@ -39,7 +39,7 @@ static_assert(kBotItems == 8, "a thread owns 8 consecutive list positions (one t
 constexpr size_t kOffList = 0;                                   // u16[2][3][8192]  lists [buffer][dim]
 constexpr size_t kOffTmpKey = kOffList + 6 * 2 * kBottomCap;     // u32[8192]        sort scratch
 constexpr size_t kOffTmpLid = kOffTmpKey + 4 * kBottomCap;       // u16[8192]
-constexpr size_t kOffHist = kOffTmpLid + 2 * kBottomCap;         // u32[4097]        (radix: u16[32][256])
+constexpr size_t kOffHist = kOffTmpLid + 2 * kBottomCap;         // u32[8193]        (radix: u16[32][256])
 constexpr size_t kOffSegPos = kOffHist + 4 * (kSortBins + 4);    // u16[8192]        sub-segment of a position
 constexpr size_t kOffSide = kOffSegPos + 2 * kBottomCap;         // u8[8192]         1 = right child
 constexpr size_t kOffTabCnt = kOffSide + kBottomCap;             // u16[1024]
@@ -306,21 +306,22 @@ __global__ void __launch_bounds__(kBotThreads, 1) bottom_kernel(BottomArgs a) {
             lr[r] = e < n ? atomicAdd(&hist[bin[r]], 1u) : 0u;
         }
         __syncthreads();
-        // exclusive scan of the bin counts (4 per thread) -> bin starts; hist[kSortBins] = n
+        // exclusive scan of the bin counts (8 per thread) -> bin starts; hist[kSortBins] = n
         bool long_run = false;
         {
-            uint32_t c[4], sum = 0;
+            constexpr int PER = kSortBins / kBotThreads;
+            uint32_t c[PER], sum = 0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                c[i] = hist[tid * 4 + i];
+            for (int i = 0; i < PER; ++i) {
+                c[i] = hist[tid * PER + i];
                 sum += c[i];
                 long_run = long_run || c[i] > kRunMax;
             }
             uint32_t total;
             uint32_t run = block_exclusive_sum(sum, misc + 8, total);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                hist[tid * 4 + i] = run;
+            for (int i = 0; i < PER; ++i) {
+                hist[tid * PER + i] = run;
                 run += c[i];
             }
             if (tid == 0) hist[kSortBins] = n;
@@ -359,7 +360,7 @@ __global__ void __launch_bounds__(kBotThreads, 1) bottom_kernel(BottomArgs a) {
             }
         }
         __syncthreads();
-#pragma unroll 1
+#pragma unroll 2
         for (int r = 0; r < kBotItems; ++r) {
             const uint32_t p = r * kBotThreads + tid;
             if (p < n) {
@@ -367,16 +368,18 @@ __global__ void __launch_bounds__(kBotThreads, 1) bottom_kernel(BottomArgs a) {
                 const uint16_t lid = tmp_lid[p];
                 const uint32_t b = bin_of(__uint_as_float(ordered_to_float(key)), lo, scale, kSortBins);
                 const uint32_t s0 = hist[b], s1 = hist[b + 1];
-                uint32_t rank = 0;
+                uint32_t lt = 0, eq = 0;
                 for (uint32_t q = s0; q < s1; ++q) {
                     const uint32_t kq = tmp_key[q];
-                    if (kq < key) {
-                        ++rank;
-                    } else if (kq == key && q != p) {
-                        if (a.id[gbase + tmp_lid[q]] < a.id[gbase + lid]) ++rank; // equal coordinates: by id
-                    }
+                    lt += kq < key ? 1u : 0u;
+                    eq += kq == key ? 1u : 0u;
                 }
-                out[s0 + rank] = lid;
+                if (eq > 1u) { // equal coordinates: by id (rare)
+                    const uint32_t my_id = a.id[gbase + lid];
+                    for (uint32_t q = s0; q < s1; ++q)
+                        if (tmp_key[q] == key && a.id[gbase + tmp_lid[q]] < my_id) ++lt;
+                }
+                out[s0 + lt] = lid;
             }
         }
         __syncthreads();
@@ -552,36 +555,49 @@ __global__ void __launch_bounds__(kBotThreads, 1) bottom_kernel(BottomArgs a) {
         if (!__syncthreads_or(splits_more ? 1 : 0)) break;
     }
 
-    // ---- the x-list is the final order: one 128-byte tile per thread ------------------------------------------
+    // ---- the x-list is the final order -------------------------------------------------------------------------
+    // pos_of = inverse of the x-list; points are read coalesced by element id, placed into staged
+    // 128-byte tiles in shared memory (over the lists and the sort keys, all dead now), copied out.
+    uint16_t *pos_of = tmp_lid;
+    float *stage = reinterpret_cast<float *>(smem);
+    static_assert(kOffTmpLid >= 16 * (size_t)kBottomCap, "staging area must end before pos_of");
     if (mine) {
         const uint4 pk = *reinterpret_cast<const uint4 *>(list_of(0, cur0) + p0);
         const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
-        float tx[8], ty[8], tz[8];
-        uint32_t ti[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const uint32_t e = (i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xFFFFu);
-            tx[i] = a.x[gbase + e];
-            ty[i] = a.y[gbase + e];
-            tz[i] = a.z[gbase + e];
-            ti[i] = a.id[gbase + e];
+        for (int i = 0; i < 4; ++i) {
+            pos_of[w[i] & 0xFFFFu] = (uint16_t)(p0 + 2 * i);
+            pos_of[w[i] >> 16] = (uint16_t)(p0 + 2 * i + 1);
+        }
+    }
+    __syncthreads();
+    {
+        float px[kBotItems], py[kBotItems], pz[kBotItems];
+        uint32_t pi[kBotItems], pp[kBotItems];
+#pragma unroll
+        for (int r = 0; r < kBotItems; ++r) {
+            const uint32_t e = r * kBotThreads + tid;
+            const bool ok = e < n;
+            px[r] = ok ? a.x[gbase + e] : 0.0f;
+            py[r] = ok ? a.y[gbase + e] : 0.0f;
+            pz[r] = ok ? a.z[gbase + e] : 0.0f;
+            pi[r] = ok ? a.id[gbase + e] : 0u;
+            pp[r] = ok ? pos_of[e] : 0u;
         }
         if (a.idx0) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) ti[i] = a.idx0[ti[i]];
+            for (int r = 0; r < kBotItems; ++r)
+                if (r * kBotThreads + tid < n) pi[r] = a.idx0[pi[r]];
         }
-        float4 *dst = reinterpret_cast<float4 *>(a.tiles + ((gbase + p0) >> 3) * 32);
-        dst[0] = make_float4(tx[0], tx[1], tx[2], tx[3]);
-        dst[1] = make_float4(tx[4], tx[5], tx[6], tx[7]);
-        dst[2] = make_float4(ty[0], ty[1], ty[2], ty[3]);
-        dst[3] = make_float4(ty[4], ty[5], ty[6], ty[7]);
-        dst[4] = make_float4(tz[0], tz[1], tz[2], tz[3]);
-        dst[5] = make_float4(tz[4], tz[5], tz[6], tz[7]);
-        dst[6] = make_float4(__uint_as_float(ti[0]), __uint_as_float(ti[1]), __uint_as_float(ti[2]),
-                             __uint_as_float(ti[3]));
-        dst[7] = make_float4(__uint_as_float(ti[4]), __uint_as_float(ti[5]), __uint_as_float(ti[6]),
-                             __uint_as_float(ti[7]));
+        __syncthreads(); // every thread has read its pos_of / list entries: the staging area may be overwritten
+#pragma unroll
+        for (int r = 0; r < kBotItems; ++r)
+            if (r * kBotThreads + tid < n) put_tile(stage, pp[r], px[r], py[r], pz[r], pi[r]);
     }
+    __syncthreads();
+    float4 *dst = reinterpret_cast<float4 *>(a.tiles + (gbase >> 3) * 32);
+    const float4 *src = reinterpret_cast<const float4 *>(stage);
+    for (uint32_t i = tid; i < n; i += kBotThreads) dst[i] = src[i]; // n points = n float4
 }
 
 } // namespace td
