@@ -273,26 +273,18 @@ inline void build_select(td::TopPlan const &plan, uint64_t n_padded, int leaf_si
             const uint32_t mc = (uint32_t)div_up(plan.biggest[l], kChunk);
             const unsigned grid = nseg * mc;
             const float *col = dim == 0 ? cur.x : (dim == 1 ? cur.y : cur.z);
-            if (plan.biggest[l] > kDirectMaxCount) {
-                // few huge segments: chunked candidate compaction, then one CTA per segment selects
-                bucket_kernel<<<(unsigned)div_up((uint64_t)nseg * 32, 256), 256, 0, stream>>>(
-                    segs_l, nseg, nb, hist_cur, sel, cursors);
-                NBK_LAUNCHED();
-                const uint32_t spans = (uint32_t)div_up(plan.biggest[l], kCompactSpan);
-                compact_kernel<<<nseg * spans, kCompactThreads, 0, stream>>>(
-                    col, cur.id, segs_l, bounds_cur, sel, dim, spans, nb, cursors, cand);
-                NBK_LAUNCHED();
-                select_kernel<false><<<nseg, 1024, 0, stream>>>(segs_l, sel, hist_cur, cursors, nb, col, cur.id,
-                                                                cand, dim, bounds_cur, bounds_alt, pivot,
-                                                                arena.nodes);
-                NBK_LAUNCHED();
-            } else {
-                // many moderate segments: the select CTA finds the bin and its candidates itself
-                select_kernel<true><<<nseg, kDirectThreads, 0, stream>>>(segs_l, sel, hist_cur, cursors, nb, col,
-                                                                         cur.id, cand, dim, bounds_cur,
-                                                                         bounds_alt, pivot, arena.nodes);
-                NBK_LAUNCHED();
-            }
+            bucket_kernel<<<(unsigned)div_up((uint64_t)nseg * 32, 256), 256, 0, stream>>>(segs_l, nseg, nb,
+                                                                                       hist_cur, sel, cursors);
+            NBK_LAUNCHED();
+            const uint32_t spans = (uint32_t)div_up(plan.biggest[l], kCompactSpan);
+            compact_kernel<<<nseg * spans, kCompactThreads, 0, stream>>>(col, cur.id, segs_l, bounds_cur, sel,
+                                                                       dim, spans, nb, cursors, cand);
+            NBK_LAUNCHED();
+            const uint64_t expect = plan.biggest[l] / nb; // candidates per segment for uniform data
+            const unsigned sel_threads = expect > 2048 ? 1024u : (expect > 128 ? 256u : 128u);
+            select_kernel<<<nseg, sel_threads, 0, stream>>>(segs_l, sel, cand, dim, bounds_cur, bounds_alt, pivot,
+                                                            arena.nodes);
+            NBK_LAUNCHED();
             if (l + 1 < T) {
                 partition_kernel<true><<<grid, kChunkThreads, 2 * nb * 4, stream>>>(
                     cur, alt, segs_l, pivot, cursors, dim, mc, segs_next, bounds_cur, nb, hist_alt);

@@ -37,8 +37,6 @@ constexpr int kChunkItems = kChunk / kChunkThreads;
 constexpr int kChunkWarps = kChunkThreads / 32;
 constexpr int kBottomCap = 8192; // largest segment the bottom kernel splits in shared memory
 constexpr int kSelectCap = 2048; // candidates sorted in shared memory by the select kernel
-constexpr uint32_t kDirectMaxCount = 65536; // levels whose segments are at most this big select directly
-constexpr int kDirectThreads = 512;
 
 // One segment of one level.  Level l has 2^l slots in heap order (children of s: 2s, 2s+1); a
 // leaf met above the bottom phase is carried down as child 2s (mid == kNoSplit), 2s+1 stays empty.
@@ -284,10 +282,12 @@ __device__ __forceinline__ uint32_t warp_scan_counters(uint32_t *cnt, int lane) 
     return __shfl_sync(0xffffffffu, incl, 31);
 }
 
-// ---- compact (top levels: few, huge segments): elements of the selected bin -> candidate list --------
-// One CTA walks kCompactSpan points of one segment; candidates are collected in shared memory and
-// appended to the segment's list with one global atomic per flush.
+// ---- compact: elements of the selected bin -> the segment's candidate list ------------------------------
+// One CTA streams kCompactSpan points of one segment without any barrier; candidates (about 1 in nb)
+// are collected in shared memory and appended to the segment's list with one global atomic at the end.
+// If the buffer overflows (clustered data) the remaining candidates are appended warp by warp.
 constexpr int kCompactThreads = 512;
+constexpr int kCompactItems = 8;
 constexpr int kCompactSpan = 32768;
 constexpr int kCompactBuf = 4096;
 __global__ void __launch_bounds__(kCompactThreads)
@@ -296,7 +296,7 @@ compact_kernel(const float *__restrict__ coord, const uint32_t *__restrict__ id,
                const Sel *__restrict__ sel, int dim, uint32_t max_spans, uint32_t nb,
                uint32_t *__restrict__ cursors, unsigned long long *__restrict__ cand) {
     __shared__ unsigned long long sbuf[kCompactBuf];
-    __shared__ uint32_t s_n, s_base;
+    __shared__ uint32_t s_n, s_fail, s_base;
     const uint32_t s = blockIdx.x / max_spans, c = blockIdx.x - s * max_spans;
     const Seg sg = segs[s];
     const uint32_t off = c * kCompactSpan;
@@ -308,71 +308,70 @@ compact_kernel(const float *__restrict__ coord, const uint32_t *__restrict__ id,
     float lo, hi;
     seg_range(bounds, s, dim, lo, hi);
     const float scale = bin_scale(lo, hi, nb);
-    if (threadIdx.x == 0) s_n = 0;
+    if (threadIdx.x == 0) {
+        s_n = 0;
+        s_fail = 0xFFFFFFFFu;
+    }
     __syncthreads();
-    constexpr int ITEMS = 4;
-    for (uint32_t sub = off; sub < end; sub += kCompactThreads * ITEMS) {
-        float v[ITEMS];
+    for (uint32_t sub = off; sub < end; sub += kCompactThreads * kCompactItems) {
+        float v[kCompactItems];
 #pragma unroll
-        for (int r = 0; r < ITEMS; ++r) {
+        for (int r = 0; r < kCompactItems; ++r) {
             const uint32_t i = sub + r * kCompactThreads + threadIdx.x;
-            v[r] = i < end ? coord[(uint64_t)sg.begin + i] : 0.0f;
+            v[r] = i < end ? __ldcs(coord + (uint64_t)sg.begin + i) : 0.0f;
         }
 #pragma unroll
-        for (int r = 0; r < ITEMS; ++r) {
+        for (int r = 0; r < kCompactItems; ++r) {
             const uint32_t i = sub + r * kCompactThreads + threadIdx.x;
             const bool f = i < end && bin_of(v[r], lo, scale, nb) == se.bin;
             const unsigned bal = __ballot_sync(0xffffffffu, f);
             if (bal) {
+                const uint32_t cnt = __popc(bal);
                 uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(&s_n, __popc(bal));
+                if (lane == 0) base = atomicAdd(&s_n, cnt);
                 base = __shfl_sync(0xffffffffu, base, 0);
-                if (f) sbuf[base + __popc(bal & lt)] = composite(v[r], id[(uint64_t)sg.begin + i]);
+                if (base + cnt <= (uint32_t)kCompactBuf) {
+                    if (f) sbuf[base + __popc(bal & lt)] = composite(v[r], id[(uint64_t)sg.begin + i]);
+                } else {
+                    uint32_t g = 0;
+                    if (lane == 0) {
+                        atomicMin(&s_fail, base);
+                        g = atomicAdd(&cursors[3 * (uint64_t)s], cnt);
+                    }
+                    g = __shfl_sync(0xffffffffu, g, 0);
+                    if (f)
+                        cand[(uint64_t)sg.begin + g + __popc(bal & lt)] =
+                            composite(v[r], id[(uint64_t)sg.begin + i]);
+                }
             }
         }
+    }
+    __syncthreads();
+    const uint32_t have = min(s_n, s_fail); // reservations are contiguous up to the first failed one
+    if (have) {
+        if (threadIdx.x == 0) s_base = atomicAdd(&cursors[3 * (uint64_t)s], have);
         __syncthreads();
-        // flush when another sub-span might not fit (uniform decision)
-        const uint32_t have = s_n;
-        const bool last = sub + kCompactThreads * ITEMS >= end;
-        if (have && (last || have + kCompactThreads * ITEMS > (uint32_t)kCompactBuf)) {
-            if (threadIdx.x == 0) s_base = atomicAdd(&cursors[3 * (uint64_t)s], have);
-            __syncthreads();
-            for (uint32_t j = threadIdx.x; j < have; j += kCompactThreads)
-                cand[(uint64_t)sg.begin + s_base + j] = sbuf[j];
-            __syncthreads();
-            if (threadIdx.x == 0) s_n = 0;
-            __syncthreads();
-        }
+        for (uint32_t j = threadIdx.x; j < have; j += kCompactThreads)
+            cand[(uint64_t)sg.begin + s_base + j] = sbuf[j];
     }
 }
-static_assert(kCompactBuf >= 2 * kCompactThreads * 4, "a sub-span must fit the buffer twice");
 
 // ---- select: exact rank among the candidates, one CTA per segment -------------------------------------
-// DIRECT (deep levels: many segments of moderate size): the CTA also does the bucket step and collects
-// the candidates itself by scanning the segment's split coordinate, so those levels need neither the
-// bucket nor the compact pass.
-template <bool DIRECT>
 __global__ void __launch_bounds__(1024)
-select_kernel(const Seg *__restrict__ segs, const Sel *__restrict__ sel, uint32_t *__restrict__ hist,
-              uint32_t *__restrict__ cursors, uint32_t nb, const float *__restrict__ coord,
-              const uint32_t *__restrict__ id, unsigned long long *__restrict__ cand, int dim,
-              const float4 *__restrict__ bounds, float4 *__restrict__ bounds_next,
-              unsigned long long *__restrict__ pivot, nbk_node *__restrict__ nodes) {
+select_kernel(const Seg *__restrict__ segs, const Sel *__restrict__ sel,
+              const unsigned long long *__restrict__ cand, int dim, const float4 *__restrict__ bounds,
+              float4 *__restrict__ bounds_next, unsigned long long *__restrict__ pivot,
+              nbk_node *__restrict__ nodes) {
     __shared__ unsigned long long sbuf[kSelectCap];
     __shared__ uint32_t sh[256];
     __shared__ unsigned long long s_red[2][32];
     __shared__ uint32_t s_pick[3]; // digit, elements before it, elements in it
     __shared__ uint32_t s_cnt;
-    __shared__ Sel s_sel;
     const uint32_t s = blockIdx.x;
     const Seg sg = segs[s];
     if (sg.count == 0) return;
     const int tid = threadIdx.x, bd = blockDim.x, lane = tid & 31, warp = tid >> 5;
     const float4 blo = bounds[2 * (uint64_t)s], bhi = bounds[2 * (uint64_t)s + 1];
-    if (DIRECT && warp == 0) {
-        const Sel out = find_bucket(sg, s, nb, hist, cursors, lane);
-        if (lane == 0) s_sel = out;
-    }
     if (sg.mid == kNoSplit) { // carried leaf: child 2s inherits the cell
         if (tid == 0) {
             bounds_next[4 * (uint64_t)s] = blo;
@@ -380,39 +379,10 @@ select_kernel(const Seg *__restrict__ segs, const Sel *__restrict__ sel, uint32_
         }
         return;
     }
-    if (tid == 0) s_cnt = 0;
-    __syncthreads();
-    const Sel se = DIRECT ? s_sel : sel[s];
-    unsigned long long *cp = cand + sg.begin;
+    const Sel se = sel[s];
+    const unsigned long long *cp = cand + sg.begin;
     const uint32_t c_all = se.c;
     uint32_t c = se.c, r = se.r;
-    bool gathered = false;
-    if (DIRECT) {
-        float lo, hi;
-        seg_range(bounds, s, dim, lo, hi);
-        const float scale = bin_scale(lo, hi, nb);
-        const bool fits = c_all <= (uint32_t)kSelectCap;
-        for (uint32_t i0 = tid; i0 < sg.count; i0 += 8u * bd) {
-            float v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const uint32_t i = i0 + u * bd;
-                v[u] = i < sg.count ? coord[(uint64_t)sg.begin + i] : 0.0f;
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const uint32_t i = i0 + u * bd;
-                if (i < sg.count && bin_of(v[u], lo, scale, nb) == se.bin) {
-                    const unsigned long long key = composite(v[u], id[(uint64_t)sg.begin + i]);
-                    const uint32_t p = atomicAdd(&s_cnt, 1u);
-                    if (fits) sbuf[p] = key;
-                    else cp[p] = key;
-                }
-            }
-        }
-        __syncthreads(); // global writes of this CTA are visible to it after the barrier
-        gathered = fits;
-    }
     unsigned long long base = 0ull, span = ~0ull;
     if (c > (uint32_t)kSelectCap) {
         unsigned long long mn = ~0ull, mx = 0ull;
@@ -473,19 +443,17 @@ select_kernel(const Seg *__restrict__ segs, const Sel *__restrict__ sel, uint32_
             __syncthreads();
         }
     }
-    if (!gathered) {
-        // gather the remaining range
-        if (tid == 0) s_cnt = 0;
-        __syncthreads();
-        for (uint32_t i = tid; i < c_all; i += bd) {
-            const unsigned long long v = cp[i];
-            if (v >= base && v - base <= span) {
-                const uint32_t p = atomicAdd(&s_cnt, 1u);
-                if (p < (uint32_t)kSelectCap) sbuf[p] = v;
-            }
+    // gather the remaining range
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < c_all; i += bd) {
+        const unsigned long long v = cp[i];
+        if (v >= base && v - base <= span) {
+            const uint32_t p = atomicAdd(&s_cnt, 1u);
+            if (p < (uint32_t)kSelectCap) sbuf[p] = v;
         }
-        __syncthreads();
     }
+    __syncthreads();
     // sort it, pick rank r
     c = min(c, (uint32_t)kSelectCap); // (never exceeded: composites are unique)
     uint32_t p2 = 1;
@@ -573,14 +541,20 @@ partition_kernel(Columns in, Columns out, const Seg *__restrict__ segs,
     float px[kChunkItems], py[kChunkItems], pz[kChunkItems];
     uint32_t pid[kChunkItems];
     uint32_t rank[kChunkItems]; // bit 31: goes left
+    // all 32 loads of the thread are issued before the first use (the pass is latency bound otherwise)
 #pragma unroll
     for (int r = 0; r < kChunkItems; ++r) {
         const uint32_t i = off + r * kChunkThreads + threadIdx.x;
         const bool ok = i < end;
-        px[r] = ok ? in.x[gbase + i] : 0.0f;
-        py[r] = ok ? in.y[gbase + i] : 0.0f;
-        pz[r] = ok ? in.z[gbase + i] : 0.0f;
-        pid[r] = ok ? in.id[gbase + i] : 0u;
+        px[r] = ok ? __ldcs(in.x + gbase + i) : 0.0f;
+        py[r] = ok ? __ldcs(in.y + gbase + i) : 0.0f;
+        pz[r] = ok ? __ldcs(in.z + gbase + i) : 0.0f;
+        pid[r] = ok ? __ldcs(in.id + gbase + i) : 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < kChunkItems; ++r) {
+        const uint32_t i = off + r * kChunkThreads + threadIdx.x;
+        const bool ok = i < end;
         const float key = dim == 0 ? px[r] : (dim == 1 ? py[r] : pz[r]);
         const bool left = ok && (!split || composite(key, pid[r]) < pk);
         const unsigned bl = __ballot_sync(0xffffffffu, left);
