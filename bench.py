@@ -65,6 +65,21 @@ def algorithmic_bytes_per_query(k, v_n, v_p):
     return 12 + 8 * k + 16 * v_n + 16 * v_p
 
 
+def ncu_traffic(args):
+    """DRAM bytes (read + write) of one kNN-kernel launch from the committed `ncu --set full` capture
+    of this workload (profiles/knn_traffic.json), or None when the run is not that workload."""
+    path = os.path.join(ROOT, "profiles", "knn_traffic.json")
+    if not os.path.exists(path):
+        return None, "no ncu capture committed"
+    with open(path) as f:
+        rec = json.load(f)
+    same = (rec.get("side") == args.side and rec.get("queries") == args.queries and rec.get("k") == args.k
+            and rec.get("leaf") == args.leaf)
+    if not same:
+        return None, "ncu capture is for another workload"
+    return rec["dram_bytes_per_launch"], rec.get("source", path)
+
+
 def measured_hbm_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -75,17 +90,20 @@ def measured_hbm_peak():
 
 # ---- clocks -------------------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi polled every 20 ms from before the warm-up; only the samples whose timestamp falls
+    inside the timed region are reported (the recipe's clocks line)."""
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index, self.proc, self.lines = index, None, []
+        self.window = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -94,28 +112,40 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark(self, t0: float, t1: float):
+        """Wall-clock bounds of the timed region."""
+        self.window = (t0, t1)
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         self.thread.join(timeout=2)
-        sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        rows = []
+        for seen, line in self.lines:
             parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[0])); mx.append(float(parts[1])); power.append(float(parts[2]))
+                rows.append((seen, float(parts[1]), float(parts[2]), float(parts[3]), parts[4:8]))
             except ValueError:
                 continue
-            for name, val in zip(names, parts[3:7]):
+        inside = [r for r in rows if self.window and self.window[0] <= r[0] <= self.window[1] + 0.03]
+        used = inside or rows
+        reasons = set()
+        for r in used:
+            for name, val in zip(names, r[4]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        sm = [r[1] for r in used]
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(r[2] for r in used) if used else None,
+                "power_w_max": max(r[3] for r in used) if used else None,
+                "samples": len(used), "samples_in_timed_region": len(inside), "reasons": sorted(reasons)}
 
 
 # ---- CPU reference (the reference's own code, oracle/_ref; or the C restatement) -------------------
@@ -185,17 +215,22 @@ def run_b200_arm(args):
     stream = torch.cuda.current_stream().cuda_stream
 
     # --- tree: built on rank 0, replicated with one NCCL broadcast --------------------------------
-    tree, build_ms, pts_host = None, None, None
+    tree, build_ms, build_all_ms, pts_host = None, None, None, None
     if rank == 0:
         g = torch.Generator(device=dev); g.manual_seed(42)
         pts = torch.rand((n, 3), device=dev, generator=g)
-        warm = capi.Tree.build_device(pts.data_ptr(), min(n, 1 << 20), args.leaf, 1.0, stream=stream)
-        warm.close()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        tree = capi.Tree.build_device(pts.data_ptr(), n, args.leaf, 1.0, stream=stream)
-        e1.record(); torch.cuda.synchronize()
-        build_ms = e0.elapsed_time(e1)
+        # one untimed full-size build (first-touch of the scratch pool), then three timed ones
+        capi.Tree.build_device(pts.data_ptr(), n, args.leaf, 1.0, stream=stream).close()
+        build_all_ms = []
+        for _ in range(3):
+            if tree is not None:
+                tree.close()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            tree = capi.Tree.build_device(pts.data_ptr(), n, args.leaf, 1.0, stream=stream)
+            e1.record(); torch.cuda.synchronize()
+            build_all_ms.append(e0.elapsed_time(e1))
+        build_ms = float(np.median(build_all_ms))
         if world == 1 and not args.no_cpu_baseline:
             pts_host = pts.cpu().numpy()
         del pts
@@ -222,22 +257,24 @@ def run_b200_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step()
+    barrier()
     capi.profile_read(capi.SECTION_KNN_KERNEL); capi.profile_read(capi.SECTION_QUERY_ORDER)
     capi.profile_enable(True)
     launches0 = capi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    wall0 = time.time()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     barrier()
+    sampler.mark(wall0, time.time())
     launches = capi.launch_count() - launches0
     capi.profile_enable(False)
     knn_ms, knn_cnt = capi.profile_read(capi.SECTION_KNN_KERNEL)
@@ -309,6 +346,7 @@ def run_b200_arm(args):
         return
 
     peak, peak_src = measured_hbm_peak()
+    traffic, traffic_src = ncu_traffic(args)
     b_q = algorithmic_bytes_per_query(k, v_n, v_p)
     knn_ms_per_launch = knn_ms / max(knn_cnt, 1)
     achieved = b_q * m / (knn_ms_per_launch * 1e-3) / 1e9
@@ -325,7 +363,8 @@ def run_b200_arm(args):
         "clocks": clocks,
         "roofline": {
             "bound": "hbm", "kernel": "knn_lane_kernel<K=8,periodic> (primary pass; the boundary pass is included in the timed section)", "achieved": achieved, "peak": peak,
-            "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+            "peak_source": peak_src,
             "algorithmic_bytes_per_query": b_q, "queries_per_launch": m, "counters": counters_source,
             "kernel_ms_per_launch": knn_ms_per_launch, "kernel_share_of_step": knn_ms / total_ms,
             "query_order_ms_per_step": order_ms / args.steps,
@@ -333,7 +372,11 @@ def run_b200_arm(args):
         "cpu_baseline": cpu_baseline,
         "parity_sample": parity,
         "build": {"ms": build_ms, "mpts_per_s": n / (build_ms * 1e-3) / 1e6 if build_ms else None,
+                  "all_ms": build_all_ms, "timing": "median of 3 builds from device-resident points (CUDA events "
+                  "around nbk_tree_build_device, host work included), after one untimed build",
                   "algorithmic_bytes": int(meta.n_levels) * int(meta.n_padded) * 32,
+                  "roofline_frac": (int(meta.n_levels) * int(meta.n_padded) * 32 / (build_ms * 1e-3) / 1e9 / peak)
+                  if build_ms else None,
                   "broadcast_ms": bcast_ms},
     }
     print(json.dumps(line), flush=True)
