@@ -11,7 +11,8 @@ The cases replay the reference's own tests:
 import numpy as np
 import pytest
 
-from helpers import Oracle, Reference, assert_parity, checker_tree, compare_knn, leaf_sets, philox
+from helpers import (Oracle, Reference, assert_parity, check_tree_invariants, checker_tree, compare_knn,
+                     leaf_sets, philox)
 
 pytestmark = pytest.mark.gpu
 
@@ -99,6 +100,80 @@ def test_tree_structure_matches_reference(gpu, n, leaf):
         assert leaf_sets(nodes, idx).keys() == leaf_sets(rnodes, ridx).keys()
         for key, val in leaf_sets(nodes, idx).items():
             assert np.array_equal(val, leaf_sets(rnodes, ridx)[key])
+
+
+def _tie_heavy_sets():
+    rng = np.random.Generator(np.random.Philox(11))
+    g = (np.arange(32, dtype=np.float32) + 0.5) / 32
+    lattice = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    blobs = np.concatenate([rng.normal(c, s, (40000, 3)) for c, s in [(0.2, 1e-3), (0.7, 1e-2), (0.5, 1e-5)]]
+                           + [rng.random((20000, 3))]).astype(np.float32)
+    return {
+        "lattice32": lattice,                                          # every coordinate takes 32 values
+        "lattice32-shuffled": lattice[rng.permutation(len(lattice))],
+        "identical": np.full((30000, 3), 0.25, np.float32),             # one value: selection by id alone
+        "clustered": np.clip(blobs, 0, 1),                              # 40000 points within 1e-4 of a centre
+        "wide-negative": ((rng.random((150000, 3)) - 0.5) * 2e6).astype(np.float32),
+        "one-million": philox(1 << 20, 9),                              # 2^20: repeated coordinates straddle medians
+    }
+
+
+@pytest.mark.parametrize("name", ["lattice32", "lattice32-shuffled", "identical", "clustered", "wide-negative",
+                                  "one-million"])
+@pytest.mark.parametrize("leaf", [16, 64])
+def test_build_invariants_under_ties_and_clustering(gpu, name, leaf):
+    """Select-and-partition build (tree_topdown.cuh / tree_bottom.cuh) on inputs where coordinates
+    repeat massively: topology from counts alone, exact rank-median splits, tuples preserved, and the
+    kNN answer equal to the reference's (tests/test_builders.cpp:65-127 strengthened)."""
+    pts = _tie_heavy_sets()[name]
+    n = len(pts)
+    tree = gpu.Tree.build(pts, leaf)
+    nodes = tree.nodes()
+    plan = gpu.plan_topology(n, leaf, 8)[0]
+    for f in ("dim", "left", "right"):
+        assert np.array_equal(nodes[f], plan[f]), f
+    x, y, z, idx = tree.points()
+    assert np.array_equal(np.sort(idx), np.arange(tree.n, dtype=np.uint32))
+    real = idx < n
+    assert np.array_equal(np.stack([x, y, z], 1)[real], pts[idx[real]])
+    check_tree_invariants(nodes, x, y, z, sample_every=1 if len(nodes) < 20000 else 5)
+    q = philox(500, 77)
+    d, i = tree.query(q, 8)
+    d_ref, i_ref = checker_tree(pts, leaf, None).query(q, 8, workers=0)
+    assert_parity(d, i, d_ref, i_ref, pts, q, None)
+
+
+@pytest.mark.parametrize("n,leaf,block", [(70000, 9000, 8), (200000, 20000, 8), (100000, 64, 16), (100000, 100, 64),
+                                          (8192, 16, 8), (8200, 64, 8), (3_000_001, 64, 8)])
+def test_build_shapes(gpu, n, leaf, block):
+    """Leaves larger than the shared-memory sub-tree limit, other block sizes, segment sizes at and
+    around the bottom kernel's capacity, and a tree whose top phase runs nine levels."""
+    pts = philox(n, 5)
+    tree = gpu.Tree.build(pts, leaf, block_size=block)
+    nodes = tree.nodes()
+    plan = gpu.plan_topology(n, leaf, block)[0]
+    for f in ("dim", "left", "right"):
+        assert np.array_equal(nodes[f], plan[f]), f
+    x, y, z, idx = tree.points()
+    assert np.array_equal(np.sort(idx), np.arange(tree.n, dtype=np.uint32))
+    check_tree_invariants(nodes, x, y, z, block=block, sample_every=1 if len(nodes) < 20000 else 7)
+    if block == 8:
+        ref = checker_tree(pts, leaf, None)
+        assert tree.size == ref.size and tree.n == ref.n
+        q = philox(300, 78)
+        d, i = tree.query(q, 4)
+        d_ref, i_ref = ref.query(q, 4, workers=0)
+        assert_parity(d, i, d_ref, i_ref, pts, q, None)
+
+
+def test_build_is_deterministic(gpu):
+    """The order in which the partition passes write a segment varies from run to run; the tree may
+    not: same node array and same point order, also under heavy ties."""
+    for pts in (philox(300000, 21), _tie_heavy_sets()["lattice32-shuffled"]):
+        a, b = gpu.Tree.build(pts, 32), gpu.Tree.build(pts, 32)
+        assert np.array_equal(a.nodes(), b.nodes())
+        for u, v in zip(a.points(), b.points()):
+            assert np.array_equal(u, v)
 
 
 def test_build_soa_with_custom_indices(gpu):
