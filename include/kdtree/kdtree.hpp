@@ -231,6 +231,26 @@ class KDTree {
         return result;
     }
 
+    //! Batched form of find_closest (extension; what PyKDTree::query does per row, pybind.cpp:111-161):
+    //! out_dist / out_idx are positions.size() x k, row-major.  If `statistics` is given it receives
+    //! the counters SUMMED over the batch.
+    template <typename Distance>
+    void find_closest_batch(tcb::span<const std::array<float, 3>> positions, size_t k, float *out_dist,
+                            uint32_t *out_idx, Distance const &distance = {},
+                            KDTreeQueryStatistics *statistics = nullptr) const {
+        const float *q = positions.empty() ? nullptr : positions.data()->data();
+        check(nbk_tree_query_ex(handle_, q, positions.size(), static_cast<int>(k), Distance::is_periodic ? 1 : 0,
+                                distance.box_size(), out_dist, out_idx));
+        if (statistics) {
+            uint64_t s[3];
+            check(nbk_tree_stats(handle_, q, positions.size(), static_cast<int>(k), Distance::is_periodic ? 1 : 0,
+                                 distance.box_size(), s));
+            statistics->nodes_visited = s[0];
+            statistics->nodes_pruned = s[1];
+            statistics->points_visited = s[2];
+        }
+    }
+
   protected:
     //! For wrappers that build the handle themselves (the pybind layer).
     KDTree(nbk_tree *handle, KDTreeConfiguration const &config) : handle_(handle), config_(config) {}

@@ -133,6 +133,22 @@ NBK_API int nbk_tree_query_device(const nbk_tree *tree, const float *d_q_aos, ui
 NBK_API int nbk_tree_query_ex(const nbk_tree *tree, const float *q_aos, uint64_t m, int k,
                               int periodic, float box_size, float *out_dist, uint32_t *out_idx);
 
+/* Fused kNN-CDF (the consumer of the (M,k) distance rows PyKDTree::query returns,
+ * pybind.cpp:179-188).  For every ks[i] (distinct, 1..64) the distance d to the ks[i]-th neighbour
+ * of every query is histogrammed on the device instead of being written out:
+ *     counts[i * n_bins + b] += #{queries : edges[b] <= d < edges[b+1]}   (last bin closed)
+ * i.e. numpy.histogram(dist[:, ks[i]-1], edges) of the rows nbk_tree_query would return, with one
+ * traversal at k = max(ks) for all of them and no per-query output traffic.  edges: n_bins + 1
+ * non-decreasing float32.  `counts` is accumulated into (the caller zeroes it). */
+NBK_API int nbk_tree_knn_cdf(const nbk_tree *tree, const float *q_aos, uint64_t m, const int *ks, int n_ks,
+                             const float *edges, int n_bins, uint64_t *counts);
+
+/* Same on DEVICE buffers (queries, edges, counts); ks is a host array.  Enqueued on `stream`; returns
+ * after the work has completed. */
+NBK_API int nbk_tree_knn_cdf_device(const nbk_tree *tree, const float *d_q_aos, uint64_t m, const int *ks,
+                                    int n_ks, const float *d_edges, int n_bins,
+                                    unsigned long long *d_counts, void *stream);
+
 /* KDTreeQueryStatistics (kdtree.hpp:124-131; kdtree.cpp:143-147) summed over m host queries:
  * out3 = {nodes_visited, nodes_pruned, points_visited} of the reference's closer-first traversal
  * (kdtree_impl.hpp:226-268) run on this tree. */
@@ -148,6 +164,11 @@ NBK_API int nbk_tree_arena(const nbk_tree *tree, void **d_arena, uint64_t *bytes
  * destination of ncclBroadcast) before querying it. */
 NBK_API nbk_tree *nbk_tree_alloc_replica(const nbk_tree_meta *meta, int device, int *status);
 
+/* A byte-identical copy of `tree` on another device of this process (peer copy over NVLink): the
+ * single-process alternative to alloc_replica + ncclBroadcast for callers that drive several GPUs
+ * from one process (the reference fans queries out to threads of one process, pybind.cpp:164-172). */
+NBK_API nbk_tree *nbk_tree_clone_to_device(const nbk_tree *tree, int device, int *status);
+
 /* ---- device-side timing of the library's own kernels (bench.py's roofline numbers) ---------- */
 enum { NBK_SECTION_QUERY_ORDER = 0, /* Morton keys + radix sort of the queries */
        NBK_SECTION_KNN_KERNEL = 1,  /* the kNN traversal kernel                */
@@ -159,6 +180,13 @@ NBK_API void nbk_profile_enable(int on);
 /* Waits for the recorded events, returns the summed duration (ms) and number of recordings of
  * `section` since the last read, and resets it. */
 NBK_API int nbk_profile_read(int section, double *total_ms, uint64_t *count);
+
+/* ---- device buffers for callers without a GPU array library (results left on the device) ------ */
+NBK_API void *nbk_device_alloc(uint64_t bytes); /* current device; NULL + nbk_last_error() on failure */
+NBK_API void nbk_device_free(void *ptr);
+/* kind: 0 = host -> device, 1 = device -> host; synchronous */
+NBK_API int nbk_device_copy(void *dst, const void *src, uint64_t bytes, int kind);
+NBK_API int nbk_device_zero(void *dst, uint64_t bytes);
 
 /* ---- pinned host staging (optional; speeds up the host-buffer entry points) ---------------- */
 NBK_API void *nbk_host_alloc(uint64_t bytes);

@@ -22,7 +22,9 @@ SYMBOLS = [
     "nbk_tree_build", "nbk_tree_build_device", "nbk_tree_build_soa", "nbk_plan_topology", "nbk_tree_free",
     "nbk_tree_get_meta", "nbk_tree_device", "nbk_tree_copy_nodes", "nbk_tree_copy_points",
     "nbk_tree_query", "nbk_tree_query_device", "nbk_tree_query_ex", "nbk_tree_stats",
-    "nbk_tree_arena", "nbk_tree_alloc_replica", "nbk_profile_enable", "nbk_profile_read",
+    "nbk_tree_knn_cdf", "nbk_tree_knn_cdf_device",
+    "nbk_tree_arena", "nbk_tree_alloc_replica", "nbk_tree_clone_to_device", "nbk_profile_enable", "nbk_profile_read",
+    "nbk_device_alloc", "nbk_device_free", "nbk_device_copy", "nbk_device_zero",
     "nbk_host_alloc", "nbk_host_free",
 ]
 
@@ -78,11 +80,20 @@ def lib() -> C.CDLL:
         L.nbk_tree_query_device.argtypes = [vp, vp, u64, i32, vp, vp, vp]
         L.nbk_tree_query_ex.argtypes = [vp, vp, u64, i32, i32, f32, vp, vp]
         L.nbk_tree_stats.argtypes = [vp, vp, u64, i32, i32, f32, vp]
+        L.nbk_tree_knn_cdf.argtypes = [vp, vp, u64, vp, i32, vp, i32, vp]
+        L.nbk_tree_knn_cdf_device.argtypes = [vp, vp, u64, vp, i32, vp, i32, vp, vp]
         L.nbk_tree_arena.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
         L.nbk_tree_alloc_replica.restype = vp
         L.nbk_tree_alloc_replica.argtypes = [C.POINTER(TreeMeta), i32, ip]
         L.nbk_profile_enable.argtypes = [i32]
         L.nbk_profile_read.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(u64)]
+        L.nbk_tree_clone_to_device.restype = vp
+        L.nbk_tree_clone_to_device.argtypes = [vp, i32, ip]
+        L.nbk_device_alloc.restype = vp
+        L.nbk_device_alloc.argtypes = [u64]
+        L.nbk_device_free.argtypes = [vp]
+        L.nbk_device_copy.argtypes = [vp, vp, u64, i32]
+        L.nbk_device_zero.argtypes = [vp, u64]
         L.nbk_host_alloc.restype = vp
         L.nbk_host_alloc.argtypes = [u64]
         L.nbk_host_free.argtypes = [vp]
@@ -116,6 +127,30 @@ def plan_topology(n_points: int, leaf_size: int = 64, block_size: int = 8, with_
     return nodes, int(n_nodes.value), int(n_levels.value)
 
 
+def device_alloc(nbytes: int) -> int:
+    p = lib().nbk_device_alloc(nbytes)
+    if not p:
+        raise NbkError(NBK_ERR_NOMEM, lib().nbk_last_error().decode())
+    return int(p)
+
+
+def device_free(ptr: int) -> None:
+    lib().nbk_device_free(C.c_void_p(ptr))
+
+
+def host_to_device(d_ptr: int, a: np.ndarray) -> None:
+    a = np.ascontiguousarray(a)
+    _check(lib().nbk_device_copy(C.c_void_p(d_ptr), _host_ptr(a), a.nbytes, 0))
+
+
+def device_to_host(out: np.ndarray, d_ptr: int) -> None:
+    _check(lib().nbk_device_copy(_host_ptr(out), C.c_void_p(d_ptr), out.nbytes, 1))
+
+
+def device_memset(d_ptr: int, nbytes: int) -> None:
+    _check(lib().nbk_device_zero(C.c_void_p(d_ptr), nbytes))
+
+
 def profile_enable(on: bool) -> None:
     lib().nbk_profile_enable(int(on))
 
@@ -134,10 +169,11 @@ def _host_ptr(a: np.ndarray):
 class Tree:
     """Owns one ``nbk_tree*``.  Host arrays are numpy; device buffers are integer addresses."""
 
-    def __init__(self, handle: int):
+    def __init__(self, handle: int, owned: bool = True):
         if not handle:
             raise ValueError("null tree handle")
         self._h = C.c_void_p(handle)
+        self._owned = owned  # False: a view of a tree owned elsewhere (the pybind object)
 
     # ---- construction ---------------------------------------------------------------------
     @classmethod
@@ -178,9 +214,17 @@ class Tree:
         _check(status.value)
         return cls(h)
 
+    def clone_to_device(self, device: int):
+        """A byte-identical replica on another GPU of this process (peer copy)."""
+        status = C.c_int(0)
+        h = lib().nbk_tree_clone_to_device(self._h, device, C.byref(status))
+        _check(status.value)
+        return type(self)(h)
+
     def close(self):
         if getattr(self, "_h", None):
-            lib().nbk_tree_free(self._h)
+            if getattr(self, "_owned", True):
+                lib().nbk_tree_free(self._h)
             self._h = None
 
     def __del__(self):
@@ -247,6 +291,21 @@ class Tree:
         """Enqueues the query on ``stream`` (a cudaStream_t as int); does not synchronise."""
         _check(lib().nbk_tree_query_device(self._h, C.c_void_p(d_q), m, k, C.c_void_p(d_out_d), C.c_void_p(d_out_i),
                                            C.c_void_p(stream)))
+
+    def knn_cdf(self, q: np.ndarray, ks, edges) -> np.ndarray:
+        """counts[i, b] = numpy.histogram(dist[:, ks[i]-1], edges)[0][b] without materialising the rows."""
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        ks = np.ascontiguousarray(ks, dtype=np.int32)
+        edges = np.ascontiguousarray(edges, dtype=np.float32)
+        counts = np.zeros((len(ks), len(edges) - 1), np.uint64)
+        _check(lib().nbk_tree_knn_cdf(self._h, _host_ptr(q), q.shape[0], _host_ptr(ks), len(ks), _host_ptr(edges),
+                                      len(edges) - 1, _host_ptr(counts)))
+        return counts
+
+    def knn_cdf_device(self, d_q: int, m: int, ks, d_edges: int, n_bins: int, d_counts: int, stream: int = 0):
+        ks = np.ascontiguousarray(ks, dtype=np.int32)
+        _check(lib().nbk_tree_knn_cdf_device(self._h, C.c_void_p(d_q), m, _host_ptr(ks), len(ks), C.c_void_p(d_edges),
+                                             n_bins, C.c_void_p(d_counts), C.c_void_p(stream)))
 
     def stats(self, q: np.ndarray, k: int = 1, periodic: int = -1, boxsize: float = 0.0) -> np.ndarray:
         q = np.ascontiguousarray(q, dtype=np.float32)

@@ -142,6 +142,11 @@ template <int K> struct TopK {
     static constexpr int kSize = K;
     static constexpr bool kShared = false;
     __device__ __forceinline__ void bind(unsigned long long *) {}
+    // f(j, d2 bits) for every rank j (0 = nearest); any order
+    template <typename F> __device__ __forceinline__ void for_each_rank(F &&f) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) f(j, hi[j]);
+    }
     __device__ __forceinline__ void write_row(uint32_t qid, int k_out, float *__restrict__ out_d,
                                               uint32_t *__restrict__ out_i) const {
         float *od = out_d + (uint64_t)qid * k_out;
@@ -228,6 +233,14 @@ template <int K> struct HeapK {
         const unsigned long long root = at(0);
         rhi = (uint32_t)(root >> 32);
         rlo = (uint32_t)root;
+    }
+    // f(j, d2 bits) for every rank j (0 = nearest), largest first; consumes the heap
+    template <typename F> __device__ __forceinline__ void for_each_rank(F &&f) {
+        for (int size = K; size > 0; --size) {
+            const unsigned long long top = at(0);
+            f(size - 1, (uint32_t)(top >> 32));
+            if (size > 1) sift_down(at(size - 1), size - 1);
+        }
     }
     __device__ __forceinline__ void write_row(uint32_t qid, int k_out, float *__restrict__ out_d,
                                               uint32_t *__restrict__ out_i) {
@@ -330,11 +343,44 @@ struct DeferList {
     uint32_t *count;
 };
 
+// Fused kNN-CDF epilogue: instead of the (M,k) rows, histogram the distance to the
+// k-th neighbour for every k in `kmask` (bit k-1) over `n_bins` bins with edges[0..n_bins]:
+// counts[rank of k in kmask][b] += 1 for edges[b] <= d < edges[b+1], the last bin closed, exactly
+// np.histogram(dist[:, k-1], edges) of the rows the query would have written.
+struct CdfArgs {
+    const float *edges;          // null: write rows
+    unsigned long long *counts;  // [popc(kmask)][n_bins]
+    unsigned long long kmask;
+    int n_bins;
+};
+
+__device__ __forceinline__ void cdf_accumulate(CdfArgs const &c, int j, uint32_t d2_bits, bool emit) {
+    // all 32 lanes arrive here together; `emit` says whether this lane has a row
+    uint32_t b = 0xFFFFFFFFu;
+    if (emit) {
+        const float d = __fsqrt_rn(__uint_as_float(d2_bits)); // postprocess, kdtree.cpp:154-156
+        if (d >= __ldg(c.edges) && d <= __ldg(c.edges + c.n_bins)) {
+            int lo = 0, hi = c.n_bins; // largest lo with edges[lo] <= d
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (__ldg(c.edges + mid) <= d) lo = mid;
+                else hi = mid;
+            }
+            b = (uint32_t)lo;
+        }
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, b);
+    if (b != 0xFFFFFFFFu && (int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+        const int row = __popcll(c.kmask & ((1ull << j) - 1ull));
+        atomicAdd(&c.counts[(uint64_t)row * c.n_bins + b], (unsigned long long)__popc(peers));
+    }
+}
+
 template <typename Top, bool PERIODIC, bool IMAGES>
 __global__ void __launch_bounds__(kQueryThreads, (IMAGES || Top::kShared) ? 1 : NBK_LANE_MIN_BLOCKS)
 knn_lane_kernel(QueryTree t, const float *__restrict__ q_aos, const uint32_t *__restrict__ order,
                 uint64_t m, int k_out, float *__restrict__ out_d, uint32_t *__restrict__ out_i,
-                DeferList defer) {
+                DeferList defer, CdfArgs cdf) {
     static_assert(PERIODIC || !IMAGES, "image shifts exist only for the periodic metric");
     uint64_t slot = (uint64_t)blockIdx.x * kQueryThreads + threadIdx.x;
     bool valid;
@@ -459,14 +505,21 @@ knn_lane_kernel(QueryTree t, const float *__restrict__ q_aos, const uint32_t *__
         lbeg = lend = 0;
     }
 
-    if (!valid) return;
+    bool emit = valid;
     if (PERIODIC && !IMAGES) {
-        if (min_shifted_root_term(qx, qy, qz, L) <= top.worst()) {
+        if (valid && min_shifted_root_term(qx, qy, qz, L) <= top.worst()) {
             defer.slots[atomicAdd(defer.count, 1u)] = (uint32_t)slot;
-            return;
+            emit = false;
         }
     }
-    top.write_row(qid, k_out, out_d, out_i);
+    if (cdf.edges) {
+        // the whole warp walks the ranks together (match_any inside)
+        top.for_each_rank([&](int j, uint32_t d2_bits) {
+            if ((cdf.kmask >> j) & 1ull) cdf_accumulate(cdf, j, d2_bits, emit);
+        });
+        return;
+    }
+    if (emit) top.write_row(qid, k_out, out_d, out_i);
 }
 
 // ---- the packet kernel -----------------------------------------------------------------------------

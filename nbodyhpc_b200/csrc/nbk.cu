@@ -272,7 +272,7 @@ inline int heap_from_k() {
 
 template <typename Top, bool P>
 void launch_lane(QueryTree const &qt, const float *d_q, const uint32_t *order, uint64_t m, int k,
-                 float *d_out_d, uint32_t *d_out_i, DeferList defer, cudaStream_t stream) {
+                 float *d_out_d, uint32_t *d_out_i, DeferList defer, CdfArgs cdf, cudaStream_t stream) {
     unsigned grid = (unsigned)div_up(m, kQueryThreads);
     size_t smem = Top::kShared ? (size_t)Top::kSize * kQueryThreads * sizeof(unsigned long long) : 0;
     auto fast = knn_lane_kernel<Top, P, false>;
@@ -281,20 +281,21 @@ void launch_lane(QueryTree const &qt, const float *d_q, const uint32_t *order, u
         NBK_CUDA(cudaFuncSetAttribute(fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         NBK_CUDA(cudaFuncSetAttribute(general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    fast<<<grid, kQueryThreads, smem, stream>>>(qt, d_q, order, m, k, d_out_d, d_out_i, defer);
+    fast<<<grid, kQueryThreads, smem, stream>>>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, cdf);
     NBK_LAUNCHED();
     if (P) {
         // queries whose search ball reaches through a face of the box (usually ~1 %): answered from
         // scratch over all relevant image shifts; the kernel reads the count on the device
-        general<<<grid, kQueryThreads, smem, stream>>>(qt, d_q, order, m, k, d_out_d, d_out_i, defer);
+        general<<<grid, kQueryThreads, smem, stream>>>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, cdf);
         NBK_LAUNCHED();
     }
 }
 
 template <int K, bool P>
 void launch_knn(QueryTree const &qt, const float *d_q, const uint32_t *order, uint64_t m, int k,
-                float *d_out_d, uint32_t *d_out_i, DeferList defer, cudaStream_t stream) {
+                float *d_out_d, uint32_t *d_out_i, DeferList defer, CdfArgs cdf, cudaStream_t stream) {
     if (use_packet_kernel()) {
+        if (cdf.edges) throw Error(NBK_ERR_INVALID, "the kNN-CDF epilogue needs the default (lane) kernel");
         unsigned grid = (unsigned)div_up(m, kQueryThreads);
         knn_packet_kernel<K, P><<<grid, kQueryThreads, 0, stream>>>(qt, d_q, order, m, k, d_out_d, d_out_i);
         NBK_LAUNCHED();
@@ -302,29 +303,30 @@ void launch_knn(QueryTree const &qt, const float *d_q, const uint32_t *order, ui
     }
     if constexpr (K >= 16) {
         if (k >= heap_from_k()) {
-            launch_lane<HeapK<K>, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, stream);
+            launch_lane<HeapK<K>, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, cdf, stream);
             return;
         }
     }
-    launch_lane<TopK<K>, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, stream);
+    launch_lane<TopK<K>, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, cdf, stream);
 }
 
 template <bool P>
 void dispatch_knn(QueryTree const &qt, const float *d_q, const uint32_t *order, uint64_t m, int k,
-                  float *d_out_d, uint32_t *d_out_i, DeferList defer, cudaStream_t stream) {
-    if (k <= 1) launch_knn<1, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, stream);
-    else if (k <= 2) launch_knn<2, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, stream);
-    else if (k <= 4) launch_knn<4, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, stream);
-    else if (k <= 8) launch_knn<8, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, stream);
-    else if (k <= 16) launch_knn<16, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, stream);
-    else if (k <= 32) launch_knn<32, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, stream);
-    else launch_knn<64, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, stream);
+                  float *d_out_d, uint32_t *d_out_i, DeferList defer, CdfArgs cdf, cudaStream_t stream) {
+    if (k <= 1) launch_knn<1, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, cdf, stream);
+    else if (k <= 2) launch_knn<2, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, cdf, stream);
+    else if (k <= 4) launch_knn<4, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, cdf, stream);
+    else if (k <= 8) launch_knn<8, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, cdf, stream);
+    else if (k <= 16) launch_knn<16, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, cdf, stream);
+    else if (k <= 32) launch_knn<32, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, cdf, stream);
+    else launch_knn<64, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, cdf, stream);
 }
 
 constexpr int kMaxK = 64;
 
 void query_device(nbk_tree const &tree, const float *d_q, uint64_t m, int k, float *d_out_d,
-                  uint32_t *d_out_i, cudaStream_t stream, int periodic = -1, float box_size = 0.0f) {
+                  uint32_t *d_out_i, cudaStream_t stream, int periodic = -1, float box_size = 0.0f,
+                  CdfArgs cdf = CdfArgs{nullptr, nullptr, 0ull, 0}) {
     if (k <= 0) throw Error(NBK_ERR_INVALID, "k must be positive integer"); // pybind.cpp:92-94
     if (k > kMaxK) throw Error(NBK_ERR_INVALID, "k > 64 is not supported by this build");
     if (m == 0) return;
@@ -359,9 +361,58 @@ void query_device(nbk_tree const &tree, const float *d_q, uint64_t m, int k, flo
         defer.count = scratch.get<uint32_t>(1);
         NBK_CUDA(cudaMemsetAsync(defer.count, 0, 4, stream));
     }
-    if (qt.periodic) dispatch_knn<true>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, stream);
-    else dispatch_knn<false>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, stream);
+    if (qt.periodic) dispatch_knn<true>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, cdf, stream);
+    else dispatch_knn<false>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, cdf, stream);
     t_knn.finish();
+}
+
+// kNN-CDF: ks may come in any order; rows of `d_counts` follow that order.  Internally rows are in
+// ascending-k order (the kernel indexes them by popcount of the mask); `perm_rows` maps them back.
+struct CdfPlan {
+    unsigned long long kmask = 0;
+    int kmax = 0;
+    std::vector<int> row_of; // row_of[i] = internal row of ks[i]
+};
+
+CdfPlan plan_cdf(const int *ks, int n_ks, int n_bins) {
+    if (!ks || n_ks <= 0) throw Error(NBK_ERR_INVALID, "ks must hold at least one k");
+    if (n_bins <= 0) throw Error(NBK_ERR_INVALID, "n_bins must be positive");
+    CdfPlan p;
+    for (int i = 0; i < n_ks; ++i) {
+        if (ks[i] <= 0) throw Error(NBK_ERR_INVALID, "k must be positive integer");
+        if (ks[i] > kMaxK) throw Error(NBK_ERR_INVALID, "k > 64 is not supported by this build");
+        if (p.kmask & (1ull << (ks[i] - 1))) throw Error(NBK_ERR_INVALID, "ks must be distinct");
+        p.kmask |= 1ull << (ks[i] - 1);
+        p.kmax = std::max(p.kmax, ks[i]);
+    }
+    p.row_of.resize(n_ks);
+    for (int i = 0; i < n_ks; ++i) p.row_of[i] = __builtin_popcountll(p.kmask & ((1ull << (ks[i] - 1)) - 1ull));
+    return p;
+}
+
+__global__ void add_rows_kernel(const unsigned long long *__restrict__ src, unsigned long long *__restrict__ dst,
+                                const int *__restrict__ row_of, int n_ks, int n_bins) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_ks * n_bins) return;
+    const int r = i / n_bins, b = i - r * n_bins;
+    dst[i] += src[(uint64_t)row_of[r] * n_bins + b];
+}
+
+// d_counts[i][b] += histogram of the ks[i]-th neighbour distance; everything on `stream`
+void knn_cdf_device(nbk_tree const &tree, const float *d_q, uint64_t m, CdfPlan const &plan, int n_ks,
+                    const float *d_edges, int n_bins, unsigned long long *d_counts, cudaStream_t stream) {
+    if (m == 0) return;
+    Scratch scratch(stream);
+    unsigned long long *tmp = scratch.get<unsigned long long>((uint64_t)n_ks * n_bins);
+    int *d_row = scratch.get<int>(n_ks);
+    NBK_CUDA(cudaMemsetAsync(tmp, 0, (uint64_t)n_ks * n_bins * 8, stream));
+    NBK_CUDA(cudaMemcpyAsync(d_row, plan.row_of.data(), n_ks * sizeof(int), cudaMemcpyHostToDevice, stream));
+    CdfArgs cdf{d_edges, tmp, plan.kmask, n_bins};
+    query_device(tree, d_q, m, plan.kmax, nullptr, nullptr, stream, -1, 0.0f, cdf);
+    const int total = n_ks * n_bins;
+    add_rows_kernel<<<(unsigned)div_up(total, 256), 256, 0, stream>>>(tmp, d_counts, d_row, n_ks, n_bins);
+    NBK_LAUNCHED();
+    NBK_CUDA(cudaStreamSynchronize(stream)); // plan.row_of must outlive the copy
 }
 
 } // namespace nbk
@@ -594,6 +645,46 @@ int nbk_tree_query_ex(const nbk_tree *tree, const float *q_aos, uint64_t m, int 
     });
 }
 
+int nbk_tree_knn_cdf_device(const nbk_tree *tree, const float *d_q_aos, uint64_t m, const int *ks, int n_ks,
+                            const float *d_edges, int n_bins, unsigned long long *d_counts, void *stream) {
+    return guarded([&] {
+        if (!tree || !d_edges || !d_counts) throw Error(NBK_ERR_INVALID, "null argument");
+        CdfPlan plan = plan_cdf(ks, n_ks, n_bins);
+        DeviceGuard guard(tree->device);
+        knn_cdf_device(*tree, d_q_aos, m, plan, n_ks, d_edges, n_bins, d_counts, static_cast<cudaStream_t>(stream));
+    });
+}
+
+int nbk_tree_knn_cdf(const nbk_tree *tree, const float *q_aos, uint64_t m, const int *ks, int n_ks,
+                     const float *edges, int n_bins, uint64_t *counts) {
+    return guarded([&] {
+        if (!tree || !edges || !counts) throw Error(NBK_ERR_INVALID, "null argument");
+        CdfPlan plan = plan_cdf(ks, n_ks, n_bins);
+        for (int b = 0; b < n_bins; ++b)
+            if (!(edges[b] <= edges[b + 1])) throw Error(NBK_ERR_INVALID, "bin edges must increase monotonically");
+        DeviceGuard guard(tree->device);
+        cudaStream_t stream = nullptr;
+        Scratch scratch(stream);
+        const uint64_t cells = (uint64_t)n_ks * n_bins;
+        float *d_edges = scratch.get<float>(n_bins + 1);
+        unsigned long long *d_counts = scratch.get<unsigned long long>(cells);
+        NBK_CUDA(cudaMemcpyAsync(d_edges, edges, (n_bins + 1) * 4, cudaMemcpyHostToDevice, stream));
+        NBK_CUDA(cudaMemsetAsync(d_counts, 0, cells * 8, stream));
+        // queries stream through the device in slices; only the histogram comes back
+        const uint64_t slice = std::min<uint64_t>(std::max<uint64_t>(m, 1), 1ull << 25);
+        float *d_q = scratch.get<float>(slice * 3);
+        for (uint64_t begin = 0; begin < m; begin += slice) {
+            const uint64_t cnt = std::min(slice, m - begin);
+            NBK_CUDA(cudaMemcpyAsync(d_q, q_aos + begin * 3, cnt * 12, cudaMemcpyHostToDevice, stream));
+            knn_cdf_device(*tree, d_q, cnt, plan, n_ks, d_edges, n_bins, d_counts, stream);
+        }
+        std::vector<unsigned long long> h(cells);
+        NBK_CUDA(cudaMemcpyAsync(h.data(), d_counts, cells * 8, cudaMemcpyDeviceToHost, stream));
+        NBK_CUDA(cudaStreamSynchronize(stream));
+        for (uint64_t i = 0; i < cells; ++i) counts[i] += h[i];
+    });
+}
+
 int nbk_tree_stats(const nbk_tree *tree, const float *q_aos, uint64_t m, int k, int periodic,
                    float box_size, uint64_t *out3) {
     return guarded([&] {
@@ -643,6 +734,26 @@ nbk_tree *nbk_tree_alloc_replica(const nbk_tree_meta *meta, int device, int *sta
     return out;
 }
 
+nbk_tree *nbk_tree_clone_to_device(const nbk_tree *tree, int device, int *status) {
+    nbk_tree *out = nullptr;
+    int st = guarded([&] {
+        if (!tree) throw Error(NBK_ERR_INVALID, "null argument");
+        require_sm100(device);
+        std::unique_ptr<nbk_tree> copy;
+        {
+            DeviceGuard guard(device);
+            copy = alloc_tree(tree->meta, device);
+            NBK_CUDA(cudaDeviceSynchronize());
+        }
+        DeviceGuard guard(tree->device);
+        NBK_CUDA(cudaDeviceSynchronize()); // the source tree is complete
+        NBK_CUDA(cudaMemcpyPeer(copy->arena, copy->device, tree->arena, tree->device, tree->meta.arena_bytes));
+        out = copy.release();
+    });
+    if (status) *status = st;
+    return out;
+}
+
 void nbk_profile_enable(int on) { g_profile.store(on ? 1 : 0); }
 
 int nbk_profile_read(int section, double *total_ms, uint64_t *count) {
@@ -665,6 +776,31 @@ int nbk_profile_read(int section, double *total_ms, uint64_t *count) {
         if (total_ms) *total_ms = total;
         if (count) *count = events.size();
     });
+}
+
+void *nbk_device_alloc(uint64_t bytes) {
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        g_error = std::string("cudaMalloc failed: ") + cudaGetErrorString(e);
+        return nullptr;
+    }
+    return p;
+}
+
+void nbk_device_free(void *ptr) {
+    if (ptr) cudaFree(ptr);
+}
+
+int nbk_device_copy(void *dst, const void *src, uint64_t bytes, int kind) {
+    return guarded([&] {
+        if (kind != 0 && kind != 1) throw Error(NBK_ERR_INVALID, "kind must be 0 (h2d) or 1 (d2h)");
+        NBK_CUDA(cudaMemcpy(dst, src, bytes, kind == 0 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost));
+    });
+}
+
+int nbk_device_zero(void *dst, uint64_t bytes) {
+    return guarded([&] { NBK_CUDA(cudaMemset(dst, 0, bytes)); });
 }
 
 void *nbk_host_alloc(uint64_t bytes) {

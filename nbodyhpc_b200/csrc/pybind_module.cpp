@@ -1,5 +1,6 @@
 // pybind11 module `_impl`: same class, argument names, defaults, property names and error
 // messages as the reference's kdtree/src/cpp/pybind.cpp:196-216, over the B200 C ABI.
+#include <cstring>
 #include <optional>
 
 #include <pybind11/numpy.h>
@@ -7,6 +8,7 @@
 #include <pybind11/stl.h>
 
 #include <kdtree/kdtree.hpp>
+#include <kdtree/kdtree_utils.hpp>
 
 namespace py = pybind11;
 
@@ -30,8 +32,31 @@ class PyKDTree : public wenda::kdtree::KDTree {
         return h;
     }
 
+    static nbk_tree *build_device(uintptr_t d_points, uint64_t n, int leaf_size, std::optional<float> box_size,
+                                  int device, uintptr_t stream) {
+        int status = NBK_OK;
+        nbk_tree *h = nbk_tree_build_device(reinterpret_cast<const float *>(d_points), n, leaf_size, 8,
+                                            box_size.has_value() ? 1 : 0, box_size.value_or(0.0f), device,
+                                            reinterpret_cast<void *>(stream), &status);
+        if (status != NBK_OK) throw std::runtime_error(nbk_last_error());
+        return h;
+    }
+
   public:
     PyKDTree(PyKDTree &&) noexcept = default;
+
+    // points already resident on the device (row-major (n,3) float32): no host round trip
+    PyKDTree(uintptr_t d_points, uint64_t n, int leaf_size, int max_threads, std::optional<float> box_size,
+             int device, uintptr_t stream)
+        : KDTree(build_device(d_points, n, leaf_size, box_size, device, stream),
+                 {.leaf_size = leaf_size, .max_threads = max_threads, .block_size = 8}),
+          periodic_(box_size.has_value()), box_size_(box_size.value_or(0.0f)) {}
+
+    static PyKDTree from_device(uintptr_t d_points, uint64_t n, int leaf_size, int max_threads,
+                                std::optional<float> box_size, int device, uintptr_t stream) {
+        py::gil_scoped_release nogil;
+        return PyKDTree(d_points, n, leaf_size, max_threads, box_size, device, stream);
+    }
 
     PyKDTree(py::array_t<float, py::array::c_style | py::array::forcecast> const &points, int leaf_size,
              int max_threads, std::optional<float> box_size, int device)
@@ -84,6 +109,43 @@ class PyKDTree : public wenda::kdtree::KDTree {
         return {dist, idx};
     }
 
+    // device buffers in, device buffers out, enqueued on `stream` (no synchronisation)
+    void query_device(uintptr_t d_q, uint64_t m, int k, uintptr_t d_dist, uintptr_t d_idx, uintptr_t stream) {
+        if (k <= 0) throw std::runtime_error("k must be positive integer");
+        py::gil_scoped_release nogil;
+        check(nbk_tree_query_device(handle_, reinterpret_cast<const float *>(d_q), m, k,
+                                    reinterpret_cast<float *>(d_dist), reinterpret_cast<uint32_t *>(d_idx),
+                                    reinterpret_cast<void *>(stream)));
+    }
+
+    // numpy.histogram(dist[:, k-1], edges) for every k in ks without materialising the rows
+    py::array_t<uint64_t> knn_cdf(py::array_t<float, py::array::c_style | py::array::forcecast> points,
+                                  std::vector<int> ks,
+                                  py::array_t<float, py::array::c_style | py::array::forcecast> edges) {
+        require_n_by_3(points);
+        if (edges.ndim() != 1 || edges.shape(0) < 2) throw std::runtime_error("edges must be a 1D array of at least 2 values");
+        const int n_bins = static_cast<int>(edges.shape(0)) - 1;
+        py::array_t<uint64_t> counts({(py::ssize_t)ks.size(), (py::ssize_t)n_bins});
+        std::memset(counts.mutable_data(), 0, sizeof(uint64_t) * ks.size() * n_bins);
+        int status;
+        {
+            py::gil_scoped_release nogil;
+            status = nbk_tree_knn_cdf(handle_, points.data(), static_cast<uint64_t>(points.shape(0)), ks.data(),
+                                      static_cast<int>(ks.size()), edges.data(), n_bins, counts.mutable_data());
+        }
+        if (status != NBK_OK) throw std::runtime_error(nbk_last_error());
+        return counts;
+    }
+
+    void knn_cdf_device(uintptr_t d_q, uint64_t m, std::vector<int> ks, uintptr_t d_edges, int n_bins,
+                        uintptr_t d_counts, uintptr_t stream) {
+        py::gil_scoped_release nogil;
+        check(nbk_tree_knn_cdf_device(handle_, reinterpret_cast<const float *>(d_q), m, ks.data(),
+                                      static_cast<int>(ks.size()), reinterpret_cast<const float *>(d_edges), n_bins,
+                                      reinterpret_cast<unsigned long long *>(d_counts),
+                                      reinterpret_cast<void *>(stream)));
+    }
+
     py::array nodes_array() const {
         auto n = nodes();
         py::list fields;
@@ -105,7 +167,27 @@ class PyKDTree : public wenda::kdtree::KDTree {
 PYBIND11_MODULE(_impl, m) {
     m.doc() = "Fast KD-tree for spatial data, including periodic boundary conditions (B200-native).";
 
+    // the C++ fixture generators of include/kdtree/kdtree_utils.hpp (host only), for the tests
+    m.def("_make_random_positions", [](uint32_t n, unsigned int seed, float boxsize) {
+        auto pts = wenda::kdtree::make_random_position_and_index<3>(n, seed, boxsize);
+        py::array_t<float> out({(py::ssize_t)n, (py::ssize_t)3});
+        float *o = out.mutable_data();
+        for (uint32_t i = 0; i < n; ++i)
+            for (int d = 0; d < 3; ++d) o[3 * i + d] = pts[i].position[d];
+        return out;
+    });
+    m.def("_fill_random_positions", [](uint32_t n, unsigned int seed) {
+        auto pts = wenda::kdtree::fill_random_positions(n, seed);
+        py::array_t<float> out({(py::ssize_t)n, (py::ssize_t)3});
+        if (n) std::memcpy(out.mutable_data(), pts.data(), sizeof(float) * 3 * n);
+        return out;
+    });
+
     py::class_<PyKDTree>(m, "KDTree")
+        // device-pointer overload first: an integer is never taken for an array
+        .def(py::init(&PyKDTree::from_device), py::arg("device_pointer"), py::arg("n"), py::arg("leafsize") = 64,
+             py::arg("max_threads") = -1, py::arg("boxsize") = std::nullopt, py::arg("device") = -1,
+             py::arg("stream") = 0)
         .def(py::init(&PyKDTree::from_points), py::arg("points"), py::arg("leafsize") = 64,
              py::arg("max_threads") = -1, py::arg("boxsize") = std::nullopt, py::arg("device") = -1)
         .def("query", &PyKDTree::query, py::arg("points"), py::arg("k") = 1, py::arg("workers") = 1)
@@ -117,5 +199,8 @@ PYBIND11_MODULE(_impl, m) {
         .def_property_readonly("device", &PyKDTree::device)
         .def_property_readonly("_handle", &PyKDTree::raw_handle)
         .def("_nodes_bytes", &PyKDTree::nodes_array)
-        .def("_stats", &PyKDTree::stats, py::arg("points"), py::arg("k") = 1);
+        .def("_stats", &PyKDTree::stats, py::arg("points"), py::arg("k") = 1)
+        .def("_query_device", &PyKDTree::query_device)
+        .def("_knn_cdf", &PyKDTree::knn_cdf, py::arg("points"), py::arg("ks"), py::arg("edges"))
+        .def("_knn_cdf_device", &PyKDTree::knn_cdf_device);
 }

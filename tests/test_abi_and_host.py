@@ -111,3 +111,17 @@ def test_shard_range_is_the_thread_pool_split():
                 assert e0 == b1 or (e0 - b0 == 0 or e1 - b1 == 0) or e0 <= b1
             if total >= world:
                 assert all(e - b == total // world for b, e in spans[:-1])
+
+
+def test_cpp_fixture_generators_match_the_reference(native):
+    """include/kdtree/kdtree_utils.hpp restates Random123's Philox4x32-10 (not vendored here): its
+    make_random_position_and_index must give the values of the reference's (kdtree_utils.hpp:16-46),
+    which the oracle's generator is pinned to (tests/test_oracle.py, golden vectors)."""
+    from helpers import Oracle
+    from nbodyhpc_b200.kdtree import _impl
+
+    for n, seed, box in [(10, 42, 1.0), (1000, 43, 2.0), (4097, 7, 1.0)]:
+        assert np.array_equal(_impl._make_random_positions(n, seed, box), Oracle.philox_points(n, seed, box))
+    # the CLI's layout (main.cpp:14-35): counter {i}, lanes 0..2 -- in (0, 1], deterministic
+    a, b = _impl._fill_random_positions(1000, 42), _impl._fill_random_positions(1000, 42)
+    assert np.array_equal(a, b) and a.min() > 0.0 and a.max() <= 1.0 and len(np.unique(a)) > 2990

@@ -54,3 +54,24 @@ def test_replica_is_byte_identical_and_shards_compose(gpu, tmp_path):
     d = np.concatenate([s["d"] for s in shards])
     i = np.concatenate([s["i"] for s in shards])
     assert np.array_equal(d.view(np.uint32), d_full.view(np.uint32)) and np.array_equal(i, i_full)
+
+
+def test_in_process_replicas_from_python(gpu):
+    """KDTree(..., devices=[...]): the tree is cloned to the other GPUs with peer copies and a
+    host-array query is split into contiguous chunks, one per GPU."""
+    import torch
+
+    from nbodyhpc_b200.kdtree import KDTree
+
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    pts, q = philox(300_000, 42), philox(100_003, 43)
+    single = KDTree(pts, leafsize=64, boxsize=1.0, device=0)
+    multi = KDTree(pts, leafsize=64, boxsize=1.0, devices=list(range(world)))
+    d1, i1 = single.query(q, k=8)
+    d2, i2 = multi.query(q, k=8)
+    assert np.array_equal(d1.view(np.uint32), d2.view(np.uint32)) and np.array_equal(i1, i2)
+    for shard in multi._shards[1:]:
+        assert np.array_equal(shard.nodes(), single.nodes())
+    assert [s.device for s in multi._shards] == list(range(world))
