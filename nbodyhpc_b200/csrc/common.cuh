@@ -7,6 +7,8 @@
 #include <cfloat>
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
+#include <vector>
 #include <stdexcept>
 #include <string>
 
@@ -40,25 +42,108 @@ extern std::atomic<uint64_t> g_launches;
 inline uint64_t div_up(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
 inline uint64_t align_up(uint64_t a, uint64_t b) { return div_up(a, b) * b; }
 
-// Stream-ordered scratch allocation (cudaMallocAsync pool: after the first call of a given size the
-// memory comes back from the pool without a device synchronisation).
+// Library-owned cache of big scratch blocks (per device).  A tree build needs several GB of scratch
+// for a few milliseconds; taking it from the driver (or from the stream-ordered pool, which re-maps
+// physical memory when block sizes interleave) costs more than the build itself, so the block of the
+// last build is kept and handed to the next one.  trim() returns it to the device.
+struct BlockCache {
+    struct Entry {
+        void *ptr;
+        uint64_t bytes;
+        int device;
+        bool busy;
+    };
+    static std::mutex &mutex() {
+        static std::mutex m;
+        return m;
+    }
+    static std::vector<Entry> &entries() {
+        static std::vector<Entry> e;
+        return e;
+    }
+    static void *acquire(uint64_t bytes) {
+        int dev = 0;
+        NBK_CUDA(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lock(mutex());
+        auto &es = entries();
+        for (auto &e : es)
+            if (!e.busy && e.device == dev && e.bytes >= bytes && e.bytes / 2 <= bytes) {
+                e.busy = true;
+                return e.ptr;
+            }
+        // no fit: drop this device's idle blocks (they are the wrong size) and take a fresh one
+        for (size_t i = 0; i < es.size();) {
+            if (!es[i].busy && es[i].device == dev) {
+                cudaFree(es[i].ptr);
+                es.erase(es.begin() + i);
+            } else {
+                ++i;
+            }
+        }
+        void *p = nullptr;
+        NBK_CUDA(cudaMalloc(&p, bytes));
+        es.push_back(Entry{p, bytes, dev, true});
+        return p;
+    }
+    static void release(void *ptr) {
+        std::lock_guard<std::mutex> lock(mutex());
+        for (auto &e : entries())
+            if (e.ptr == ptr) e.busy = false;
+    }
+    static void trim(int device) {
+        std::lock_guard<std::mutex> lock(mutex());
+        auto &es = entries();
+        for (size_t i = 0; i < es.size();) {
+            if (!es[i].busy && es[i].device == device) {
+                cudaFree(es[i].ptr);
+                es.erase(es.begin() + i);
+            } else {
+                ++i;
+            }
+        }
+    }
+};
+
+// Scratch for one call.  get() takes stream-ordered allocations from the cudaMallocAsync pool;
+// reserve(bytes) first makes the following get() calls carve one block from the BlockCache instead
+// (the caller must have synchronised `stream` with the last use before the Scratch dies: the
+// destructor synchronises it to be safe).
 struct Scratch {
     cudaStream_t stream;
     void *ptrs[32];
     int count = 0;
+    char *block = nullptr;
+    uint64_t block_bytes = 0, block_used = 0, total_bytes = 0;
     explicit Scratch(cudaStream_t s) : stream(s) {}
     Scratch(Scratch const &) = delete;
+    static uint64_t padded(uint64_t bytes) { return (bytes + 255) / 256 * 256; }
+    void reserve(uint64_t bytes) {
+        if (block || bytes == 0) return;
+        block = static_cast<char *>(BlockCache::acquire(bytes));
+        block_bytes = bytes;
+        total_bytes += bytes;
+    }
     template <typename T> T *get(uint64_t n) {
-        void *p = nullptr;
         uint64_t bytes = n * sizeof(T);
         if (bytes == 0) bytes = sizeof(T);
+        if (block && block_used + padded(bytes) <= block_bytes) {
+            T *p = reinterpret_cast<T *>(block + block_used);
+            block_used += padded(bytes);
+            return p;
+        }
+        void *p = nullptr;
         NBK_CUDA(cudaMallocAsync(&p, bytes, stream));
         if (count >= 32) throw Error(NBK_ERR_INVALID, "scratch table overflow");
         ptrs[count++] = p;
+        total_bytes += bytes;
         return static_cast<T *>(p);
     }
     ~Scratch() {
         for (int i = count - 1; i >= 0; --i) cudaFreeAsync(ptrs[i], stream);
+        if (block) {
+            cudaStreamSynchronize(stream);
+            BlockCache::release(block);
+        }
     }
 };
 

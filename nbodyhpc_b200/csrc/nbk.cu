@@ -1,5 +1,6 @@
 // libnbk.so -- C ABI (include/nbk.h) over the sm_100a build and query kernels.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -141,7 +142,7 @@ std::unique_ptr<nbk_tree> alloc_tree(nbk_tree_meta const &meta, int device) {
 // n_padded points, perm holds the identity, bounds6 the orderable bounding box.
 std::unique_ptr<nbk_tree> finish_build(uint64_t n, uint64_t n_padded, int leaf_size, int block_size,
                                        int periodic, float box_size, float *x0, float *y0, float *z0,
-                                       const uint32_t *idx0,
+                                       const uint32_t *idx0, bool &trim_after,
                                        uint32_t *perm, const uint32_t *d_bounds6, int device,
                                        cudaStream_t stream) {
     // NBK_BUILD=sort selects the per-level radix-sort build (cross-check); default: select + partition
@@ -160,28 +161,31 @@ std::unique_ptr<nbk_tree> finish_build(uint64_t n, uint64_t n_padded, int leaf_s
     meta.box_size = periodic ? box_size : 0.0f;
     meta.n_levels = top.n_levels;
     auto tree = alloc_tree(meta, device);
+    uint64_t scratch_bytes = n_padded * 16; // the caller's columns
     if (sort_build) {
         TopologyPlan plan = plan_topology(n_padded, leaf_size, block_size);
         build_levels(plan, n_padded, x0, y0, z0, idx0, perm, tree->view, stream);
+        scratch_bytes += n_padded * 32;
     } else {
-        build_select(top, n_padded, leaf_size, block_size, x0, y0, z0, perm, idx0, d_bounds6,
-                     tree->view, stream);
+        scratch_bytes += build_select(top, n_padded, leaf_size, block_size, x0, y0, z0, perm, idx0, d_bounds6,
+                                      tree->view, stream);
     }
     uint32_t b[6];
     NBK_CUDA(cudaMemcpyAsync(b, d_bounds6, sizeof b, cudaMemcpyDeviceToHost, stream));
     NBK_CUDA(cudaStreamSynchronize(stream));
     {
         // A big build's scratch (several times the tree) goes back to the device so that query outputs
-        // can use it; small ones stay cached in the pool, which makes the next build allocation-free.
-        cudaMemPool_t pool;
-        int dev = 0;
-        NBK_CUDA(cudaGetDevice(&dev));
-        NBK_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
-        uint64_t reserved = 0;
+        // can use it; a small one stays cached in the pool, which makes the next build allocation-free.
         size_t free_b = 0, total_b = 0;
-        NBK_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved));
         NBK_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        if (reserved > total_b / 8) NBK_CUDA(cudaMemPoolTrimTo(pool, 0));
+        trim_after = scratch_bytes > total_b / 8;
+        if (trim_after) {
+            cudaMemPool_t pool;
+            int dev = 0;
+            NBK_CUDA(cudaGetDevice(&dev));
+            NBK_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+            NBK_CUDA(cudaMemPoolTrimTo(pool, 0));
+        }
     }
     for (int d = 0; d < 3; ++d) {
         bool empty = b[d] == 0xFFFFFFFFu && b[3 + d] == 0u;
@@ -196,29 +200,50 @@ std::unique_ptr<nbk_tree> finish_build(uint64_t n, uint64_t n_padded, int leaf_s
 std::unique_ptr<nbk_tree> build_from_device_aos(const float *d_aos, uint64_t n, int leaf_size,
                                                 int block_size, int periodic, float box_size,
                                                 int device, cudaStream_t stream) {
+    const auto host0 = std::chrono::steady_clock::now();
+    struct Trace {
+        std::chrono::steady_clock::time_point t0;
+        ~Trace() {
+            const char *v = std::getenv("NBK_BUILD_TRACE");
+            if (v && v[0] == '1')
+                fprintf(stderr, "[nbk build] whole call (ingest + plan + build + pool policy): %.3f ms host\n",
+                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+        }
+    } trace_whole{host0};
     check_build_args(n, block_size, false);
     uint64_t n_padded = div_up(n, block_size) * block_size; // pybind.cpp:23
     check_build_args(n_padded, block_size, false);
-    Scratch scratch(stream);
-    uint64_t cols = std::max<uint64_t>(n_padded, 1);
-    float *x0 = scratch.get<float>(cols), *y0 = scratch.get<float>(cols), *z0 = scratch.get<float>(cols);
-    uint32_t *perm = scratch.get<uint32_t>(cols);
-    uint32_t *aux = scratch.get<uint32_t>(8); // [0] flags, [1..6] bounds
-    const uint32_t init[8] = {0u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u, 0u};
-    NBK_CUDA(cudaMemcpyAsync(aux, init, sizeof init, cudaMemcpyHostToDevice, stream));
-    if (n_padded) {
-        ingest_aos_kernel<<<(unsigned)std::min<uint64_t>(div_up(n_padded, 256), 148 * 16), 256, 0, stream>>>(
-            d_aos, n, n_padded, x0, y0, z0, perm, periodic, box_size, aux, aux + 1);
-        NBK_LAUNCHED();
+    bool trim_after = false;
+    std::unique_ptr<nbk_tree> tree;
+    {
+        Scratch scratch(stream);
+        uint64_t cols = std::max<uint64_t>(n_padded, 1);
+        scratch.reserve(4 * Scratch::padded(cols * 4) + 256);
+        float *x0 = scratch.get<float>(cols), *y0 = scratch.get<float>(cols), *z0 = scratch.get<float>(cols);
+        uint32_t *perm = scratch.get<uint32_t>(cols);
+        uint32_t *aux = scratch.get<uint32_t>(8); // [0] flags, [1..6] bounds
+        const uint32_t init[8] = {0u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u, 0u};
+        NBK_CUDA(cudaMemcpyAsync(aux, init, sizeof init, cudaMemcpyHostToDevice, stream));
+        if (n_padded) {
+            ingest_aos_kernel<<<(unsigned)std::min<uint64_t>(div_up(n_padded, 256), 148 * 16), 256, 0, stream>>>(
+                d_aos, n, n_padded, x0, y0, z0, perm, periodic, box_size, aux, aux + 1);
+            NBK_LAUNCHED();
+        }
+        uint32_t flags = 0;
+        NBK_CUDA(cudaMemcpyAsync(&flags, aux, 4, cudaMemcpyDeviceToHost, stream));
+        NBK_CUDA(cudaStreamSynchronize(stream));
+        if (flags & 1u) // pybind.cpp:42-46
+            throw Error(NBK_ERR_INVALID, "When using periodic boundary conditions, all points must be "
+                                         "within the box (0 <= x <= box_size).");
+        tree = finish_build(n, n_padded, leaf_size, block_size, periodic, box_size, x0, y0, z0, nullptr,
+                            trim_after, perm, aux + 1, device, stream);
     }
-    uint32_t flags = 0;
-    NBK_CUDA(cudaMemcpyAsync(&flags, aux, 4, cudaMemcpyDeviceToHost, stream));
-    NBK_CUDA(cudaStreamSynchronize(stream));
-    if (flags & 1u) // pybind.cpp:42-46
-        throw Error(NBK_ERR_INVALID, "When using periodic boundary conditions, all points must be "
-                                     "within the box (0 <= x <= box_size).");
-    return finish_build(n, n_padded, leaf_size, block_size, periodic, box_size, x0, y0, z0, nullptr,
-                        perm, aux + 1, device, stream);
+    if (trim_after) {
+        int dev = 0;
+        NBK_CUDA(cudaGetDevice(&dev));
+        BlockCache::trim(dev);
+    }
+    return tree;
 }
 
 // ---- optional event timing of sections ------------------------------------------------------------
@@ -486,25 +511,34 @@ nbk_tree *nbk_tree_build_soa(const float *x, const float *y, const float *z, con
         require_sm100(device);
         DeviceGuard guard(device);
         cudaStream_t stream = nullptr;
-        Scratch scratch(stream);
-        uint64_t cols = std::max<uint64_t>(n_padded, 1);
-        float *x0 = scratch.get<float>(cols), *y0 = scratch.get<float>(cols), *z0 = scratch.get<float>(cols);
-        uint32_t *idx0 = scratch.get<uint32_t>(cols), *perm = scratch.get<uint32_t>(cols);
-        uint32_t *aux = scratch.get<uint32_t>(8);
-        const uint32_t init[8] = {0u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u, 0u};
-        NBK_CUDA(cudaMemcpyAsync(aux, init, sizeof init, cudaMemcpyHostToDevice, stream));
-        NBK_CUDA(cudaMemcpyAsync(x0, x, n_padded * 4, cudaMemcpyHostToDevice, stream));
-        NBK_CUDA(cudaMemcpyAsync(y0, y, n_padded * 4, cudaMemcpyHostToDevice, stream));
-        NBK_CUDA(cudaMemcpyAsync(z0, z, n_padded * 4, cudaMemcpyHostToDevice, stream));
-        NBK_CUDA(cudaMemcpyAsync(idx0, idx, n_padded * 4, cudaMemcpyHostToDevice, stream));
-        if (n_padded) {
-            scan_soa_kernel<<<(unsigned)std::min<uint64_t>(div_up(n_padded, 256), 148 * 16), 256, 0, stream>>>(x0, y0, z0, n_padded,
-                                                                               perm, aux + 1);
-            NBK_LAUNCHED();
+        bool trim_after = false;
+        {
+            Scratch scratch(stream);
+            uint64_t cols = std::max<uint64_t>(n_padded, 1);
+            scratch.reserve(5 * Scratch::padded(cols * 4) + 256);
+            float *x0 = scratch.get<float>(cols), *y0 = scratch.get<float>(cols), *z0 = scratch.get<float>(cols);
+            uint32_t *idx0 = scratch.get<uint32_t>(cols), *perm = scratch.get<uint32_t>(cols);
+            uint32_t *aux = scratch.get<uint32_t>(8);
+            const uint32_t init[8] = {0u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u, 0u};
+            NBK_CUDA(cudaMemcpyAsync(aux, init, sizeof init, cudaMemcpyHostToDevice, stream));
+            NBK_CUDA(cudaMemcpyAsync(x0, x, n_padded * 4, cudaMemcpyHostToDevice, stream));
+            NBK_CUDA(cudaMemcpyAsync(y0, y, n_padded * 4, cudaMemcpyHostToDevice, stream));
+            NBK_CUDA(cudaMemcpyAsync(z0, z, n_padded * 4, cudaMemcpyHostToDevice, stream));
+            NBK_CUDA(cudaMemcpyAsync(idx0, idx, n_padded * 4, cudaMemcpyHostToDevice, stream));
+            if (n_padded) {
+                scan_soa_kernel<<<(unsigned)std::min<uint64_t>(div_up(n_padded, 256), 148 * 16), 256, 0, stream>>>(
+                    x0, y0, z0, n_padded, perm, aux + 1);
+                NBK_LAUNCHED();
+            }
+            out = finish_build(n_padded, n_padded, leaf_size, block_size, periodic, box_size, x0, y0, z0, idx0,
+                               trim_after, perm, aux + 1, device, stream)
+                      .release();
         }
-        out = finish_build(n_padded, n_padded, leaf_size, block_size, periodic, box_size, x0, y0, z0,
-                           idx0, perm, aux + 1, device, stream)
-                  .release();
+        if (trim_after) {
+            int dev = 0;
+            NBK_CUDA(cudaGetDevice(&dev));
+            BlockCache::trim(dev);
+        }
     });
     if (status) *status = st;
     return out;

@@ -10,6 +10,7 @@
 // element the reference selects, and its coordinate is the node's split.
 #pragma once
 
+#include <chrono>
 #include <vector>
 
 #include "common.cuh"
@@ -218,7 +219,7 @@ struct TreeArena {
 // (x0,y0,z0[,idx0]) into the arena and fills the node array.  perm must hold the identity on entry;
 // the four columns are used as one of the two ping-pong buffers.  Everything is enqueued on `stream`
 // without host synchronisation except the final error check.
-inline void build_select(td::TopPlan const &plan, uint64_t n_padded, int leaf_size, int block_size,
+inline uint64_t build_select(td::TopPlan const &plan, uint64_t n_padded, int leaf_size, int block_size,
                          float *x0, float *y0, float *z0, uint32_t *perm, const uint32_t *idx0,
                          const uint32_t *d_bounds6, TreeArena const &arena, cudaStream_t stream) {
     using namespace td;
@@ -226,7 +227,7 @@ inline void build_select(td::TopPlan const &plan, uint64_t n_padded, int leaf_si
         const nbk_node leaf{-1, 0.0f, 0u, 0u};
         NBK_CUDA(cudaMemcpyAsync(arena.nodes, &leaf, sizeof leaf, cudaMemcpyHostToDevice, stream));
         NBK_CUDA(cudaStreamSynchronize(stream));
-        return;
+        return 0;
     }
     static const uint32_t nb = [] {
         const char *v = std::getenv("NBK_BUILD_BINS");
@@ -234,7 +235,28 @@ inline void build_select(td::TopPlan const &plan, uint64_t n_padded, int leaf_si
         return (n >= 32 && n <= 2048 && (n & (n - 1)) == 0) ? n : 256u;
     }();
     const int T = plan.top_levels;
+    // NBK_BUILD_TRACE=1: per-phase device times (CUDA events) and host wall clock on stderr
+    static const bool trace = [] {
+        const char *v = std::getenv("NBK_BUILD_TRACE");
+        return v && v[0] == '1';
+    }();
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    const auto host0 = std::chrono::steady_clock::now();
+    if (trace) {
+        for (auto &e : ev) NBK_CUDA(cudaEventCreate(&e));
+        NBK_CUDA(cudaEventRecord(ev[0], stream));
+    }
     Scratch scratch(stream);
+    {
+        const uint64_t max_segs = T > 0 ? (uint64_t)1 << (T - 1) : 0;
+        uint64_t bytes = Scratch::padded(plan.segs.size() * sizeof(Seg)) + Scratch::padded(plan.lut.size() * 4) + 256;
+        if (T > 0)
+            bytes += 4 * Scratch::padded(n_padded * 4) + Scratch::padded(n_padded * 8) +
+                     2 * Scratch::padded(max_segs * nb * 4) + Scratch::padded(max_segs * sizeof(Sel)) +
+                     Scratch::padded(max_segs * 8) + Scratch::padded(3 * max_segs * 4) +
+                     2 * Scratch::padded(4 * max_segs * sizeof(float4));
+        scratch.reserve(bytes);
+    }
     Seg *d_segs = scratch.get<Seg>(plan.segs.size());
     uint32_t *d_lut = scratch.get<uint32_t>(plan.lut.size());
     uint32_t *d_err = scratch.get<uint32_t>(1);
@@ -298,6 +320,7 @@ inline void build_select(td::TopPlan const &plan, uint64_t n_padded, int leaf_si
             std::swap(bounds_cur, bounds_alt);
         }
     }
+    if (trace) NBK_CUDA(cudaEventRecord(ev[1], stream));
     BottomArgs args;
     args.x = cur.x;
     args.y = cur.y;
@@ -321,10 +344,24 @@ inline void build_select(td::TopPlan const &plan, uint64_t n_padded, int leaf_si
     (void)attr_set;
     bottom_kernel<<<args.nseg, kBotThreads, kBottomSmem, stream>>>(args);
     NBK_LAUNCHED();
+    if (trace) NBK_CUDA(cudaEventRecord(ev[2], stream));
+    const auto host1 = std::chrono::steady_clock::now();
     uint32_t err = 0;
     NBK_CUDA(cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, stream));
     NBK_CUDA(cudaStreamSynchronize(stream)); // also keeps the plan's host tables alive long enough
+    if (trace) {
+        float top_ms = 0, bottom_ms = 0;
+        cudaEventElapsedTime(&top_ms, ev[0], ev[1]);
+        cudaEventElapsedTime(&bottom_ms, ev[1], ev[2]);
+        const double enq = std::chrono::duration<double, std::milli>(host1 - host0).count();
+        const double all = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host0).count();
+        fprintf(stderr, "[nbk build] n=%llu top_levels=%d: top %.3f ms, bottom %.3f ms (device); host enqueue %.3f ms, "
+                        "host total %.3f ms; scratch %.1f MB in %d allocation(s)\n", (unsigned long long)n_padded, T,
+                top_ms, bottom_ms, enq, all, scratch.total_bytes / 1e6, scratch.count);
+        for (auto &e : ev) cudaEventDestroy(e);
+    }
     if (err) throw Error(NBK_ERR_CUDA, "kd-tree build: sub-tree deeper than the bottom kernel's tables");
+    return scratch.total_bytes;
 }
 
 // Sort-based build (NBK_BUILD=sort; the first implementation, kept as the cross-check of the

@@ -102,7 +102,36 @@ def check(points, q, out_d, out_i, k, box, n_real, sample=256, chunk=None):
     return res
 
 
-def run(name, points, queries, ks, leaf, box, do_check=True, reps=3):
+def run_cdf(tree, queries, ks, rows_kmax, kmax, stream):
+    """Fused kNN-CDF (nbk_tree_knn_cdf_device) vs the histogram of the rows of the k = max(ks) query."""
+    m = queries.shape[0]
+    hi = float(rows_kmax[:, kmax - 1].max())
+    edges = torch.cat([torch.zeros(1, device=DEV), torch.logspace(np.log10(hi) - 3.0, np.log10(hi), 64, device=DEV)])
+    edges[-1] = hi
+    edges = edges.float().contiguous()
+    n_bins = edges.numel() - 1
+    times = []
+    for _ in range(3):
+        counts = torch.zeros((len(ks), n_bins), device=DEV, dtype=torch.int64)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        tree.knn_cdf_device(queries.data_ptr(), m, ks, edges.data_ptr(), n_bins, counts.data_ptr(), stream)
+        b.record(); torch.cuda.synchronize()
+        times.append(a.elapsed_time(b))
+    ok = True
+    for row, k in enumerate(ks):
+        d = rows_kmax[:, k - 1].contiguous()
+        # numpy.histogram semantics: [e_b, e_b+1), last bin closed
+        b_idx = torch.searchsorted(edges, d, right=True) - 1
+        b_idx[d == edges[-1]] = n_bins - 1
+        inside = (b_idx >= 0) & (b_idx < n_bins) & (d <= edges[-1])
+        expect = torch.bincount(b_idx[inside], minlength=n_bins)
+        ok = ok and bool(torch.equal(expect, counts[row]))
+    return {"cdf_ks": ks, "bins": n_bins, "ms": min(times), "mq_per_s": m / min(times) / 1e3,
+            "equals_histogram_of_rows": ok}
+
+
+def run(name, points, queries, ks, leaf, box, do_check=True, reps=3, cdf=False):
     n, m = points.shape[0], queries.shape[0]
     stream = torch.cuda.current_stream().cuda_stream
     torch.cuda.synchronize()
@@ -130,6 +159,9 @@ def run(name, points, queries, ks, leaf, box, do_check=True, reps=3):
             row["check"] = check(points, queries, od, oi, k, box, n)
         out["queries"].append(row)
         print(json.dumps({"config": name, **row}), flush=True)
+        if cdf and k == max(ks):
+            out["cdf"] = run_cdf(tree, queries, ks, od, k, stream)
+            print(json.dumps({"config": name, **out["cdf"]}), flush=True)
         del od, oi
     tree.close()
     return out
@@ -152,7 +184,7 @@ def main():
     if "4" in todo:  # clustered
         p = zeldovich(512, 42)
         results.append(run("4: 512^3 Zel'dovich periodic, 1e8 uniform queries", p, uniform(100_000_000, 43),
-                           [1, 2, 4, 8, 16, 32], 64, 1.0))
+                           [1, 2, 4, 8, 16, 32], 64, 1.0, cdf=True))
         del p
     if "5" in todo:  # HBM sizing
         p = uniform(1024 ** 3, 42)
