@@ -375,7 +375,14 @@ void query_device(nbk_tree const &tree, const float *d_q, uint64_t m, int k, flo
                                                                    scale[0], scale[1], scale[2],
                                                                    keys_a, vals_a);
     NBK_LAUNCHED();
-    int where = rs::sort_pairs<uint32_t>(keys_a, vals_a, keys_b, vals_b, m, 0, 30, work, stream);
+    // the lowest two bits per axis only order queries inside one 1/256-box cell (a leaf spans several
+    // cells at any realistic density): three 8-bit passes over bits [6, 30) instead of four
+    static const int first_bit = [] {
+        const char *v = std::getenv("NBK_MORTON_FIRST_BIT");
+        const int b = v ? std::atoi(v) : 6;
+        return (b >= 0 && b < 30) ? b : 6;
+    }();
+    int where = rs::sort_pairs<uint32_t>(keys_a, vals_a, keys_b, vals_b, m, first_bit, 30, work, stream);
     const uint32_t *order = where ? vals_b : vals_a;
     t_order.finish();
     SectionTimer t_knn(NBK_SECTION_KNN_KERNEL, stream);
@@ -638,7 +645,14 @@ int nbk_tree_query_ex(const nbk_tree *tree, const float *q_aos, uint64_t m, int 
             return n ? n : (1ull << 24);
         }();
         const uint64_t slice = std::min<uint64_t>(m, slice_cfg);
-        const int nbuf = (int)std::min<uint64_t>(3, div_up(m, slice));
+        // the first slices are smaller (2^21, 2^22, ...) so that the result download -- the bottleneck of
+        // the pipeline over PCIe -- starts after a few milliseconds instead of after a whole slice
+        static const uint64_t first_slice = [] {
+            const char *v = std::getenv("NBK_HOST_FIRST_SLICE");
+            uint64_t n = v ? std::strtoull(v, nullptr, 10) : 0;
+            return n ? n : (1ull << 21);
+        }();
+        const int nbuf = (int)std::min<uint64_t>(3, div_up(m, std::min(slice, first_slice)));
         cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
         float *d_q[3] = {}, *d_d[3] = {};
         uint32_t *d_i[3] = {};
@@ -660,8 +674,9 @@ int nbk_tree_query_ex(const nbk_tree *tree, const float *q_aos, uint64_t m, int 
                 NBK_CUDA(cudaMallocAsync(&d_i[s], slice * (uint64_t)k * 4, streams[s]));
             }
             int s = 0;
-            for (uint64_t begin = 0; begin < m; begin += slice, s = (s + 1) % nbuf) {
-                uint64_t cnt = std::min(slice, m - begin);
+            uint64_t step = std::min(slice, first_slice);
+            for (uint64_t begin = 0; begin < m; s = (s + 1) % nbuf) {
+                const uint64_t cnt = std::min(step, m - begin);
                 cudaStream_t st = streams[s];
                 NBK_CUDA(cudaMemcpyAsync(d_q[s], q_aos + begin * 3, cnt * 12, cudaMemcpyHostToDevice, st));
                 query_device(*tree, d_q[s], cnt, k, d_d[s], d_i[s], st, periodic, box_size);
@@ -669,6 +684,8 @@ int nbk_tree_query_ex(const nbk_tree *tree, const float *q_aos, uint64_t m, int 
                                          cudaMemcpyDeviceToHost, st));
                 NBK_CUDA(cudaMemcpyAsync(out_idx + begin * k, d_i[s], cnt * (uint64_t)k * 4,
                                          cudaMemcpyDeviceToHost, st));
+                begin += cnt;
+                step = std::min(slice, step * 2);
             }
             for (int t = 0; t < nbuf; ++t) NBK_CUDA(cudaStreamSynchronize(streams[t]));
         } catch (...) {
