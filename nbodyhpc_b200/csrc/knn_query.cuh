@@ -268,7 +268,6 @@ template <typename Top, bool PERIODIC>
 __device__ __forceinline__ void scan_half_tile(const float4 *g, float qx, float qy, float qz, float L,
                                                float wrap_d2, bool dedupe, Top &top) {
     const float4 X = __ldg(g), Y = __ldg(g + 2), Z = __ldg(g + 4);
-    const uint4 I = __ldg(reinterpret_cast<const uint4 *>(g + 6));
     float d[4];
     d2x4<false>(X, Y, Z, qx, qy, qz, L, d);
     if (PERIODIC) {
@@ -280,6 +279,10 @@ __device__ __forceinline__ void scan_half_tile(const float4 *g, float qx, float 
     }
     const float dmin = fminf(fminf(d[0], d[1]), fminf(d[2], d[3]));
     if (dmin <= top.worst()) {
+        // the indices are needed by about one half-tile in five: loading them here (same 128-byte line
+        // as the coordinates, an L1 hit) instead of up front takes a quarter off the L1 wavefronts, which
+        // ncu shows at 76 % of peak -- the kernel's co-limiter next to instruction issue
+        const uint4 I = __ldg(reinterpret_cast<const uint4 *>(g + 6));
         const uint32_t idx[4] = {I.x, I.y, I.z, I.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {

@@ -26,12 +26,12 @@
 namespace nbk {
 namespace td {
 
-constexpr int kBotThreads = 1024;
+constexpr int kBotThreads = kBottomCap / 8;
 constexpr int kBotWarps = kBotThreads / 32;
 constexpr int kBotItems = kBottomCap / kBotThreads; // 8 = one tile / one block_size unit per thread
-constexpr int kBotMaxIds = 1024;                    // heap ids of sub-segments: 10 levels
+constexpr int kBotMaxIds = kBottomCap / 8;          // heap ids of sub-segments (leaves hold >= 16 points)
 constexpr uint16_t kNoSplit16 = 0xFFFFu;
-constexpr uint32_t kSortBins = 8192;
+constexpr uint32_t kSortBins = kBottomCap;
 constexpr uint32_t kRunMax = 64;
 static_assert(kBotItems == 8, "a thread owns 8 consecutive list positions (one tile)");
 
@@ -54,6 +54,7 @@ constexpr size_t kBottomSmem = kOffMisc + 4 * 80;
 // the x and y lists (contiguous 32 KB), lidB over the second buffer of the z list, idord over segpos:
 // all unused while sorting
 static_assert(kBottomSmem <= 227 * 1024, "bottom kernel shared memory");
+static_assert(kBotThreads % 32 == 0 && kBotThreads <= 1024 && kSortBins % kBotThreads == 0, "bottom kernel geometry");
 
 // ---- radix fallback (stable, 8 bits per pass) ----------------------------------------------------------
 // Lanes of the warp holding the same digit.  One ballot per bit: the MATCH.ANY instruction
@@ -179,7 +180,7 @@ __device__ __noinline__ void block_sort(uint32_t *keyA, uint32_t *keyB, uint16_t
     __syncthreads();
 }
 
-// Block-wide exclusive prefix sum of one uint32 per thread (1024 threads); wsum: u32[32] scratch.
+// Block-wide exclusive prefix sum of one uint32 per thread; wsum: u32[32] scratch.
 __device__ __forceinline__ uint32_t block_exclusive_sum(uint32_t v, uint32_t *wsum, uint32_t &total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t incl = v;
@@ -190,7 +191,7 @@ __device__ __forceinline__ uint32_t block_exclusive_sum(uint32_t v, uint32_t *ws
     }
     if (lane == 31) wsum[warp] = incl;
     __syncthreads();
-    const uint32_t w = wsum[lane];
+    const uint32_t w = lane < kBotWarps ? wsum[lane] : 0u;
     uint32_t winc = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -226,7 +227,7 @@ __device__ __forceinline__ void put_tile(float *tiles, uint64_t p, float x, floa
     f[24] = __uint_as_float(idx);
 }
 
-__global__ void __launch_bounds__(kBotThreads, 1) bottom_kernel(BottomArgs a) {
+__global__ void __launch_bounds__(kBotThreads, kBotThreads <= 512 ? 2 : 1) bottom_kernel(BottomArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const Seg sg = a.segs[blockIdx.x];
     if (sg.count == 0) return;
@@ -294,8 +295,8 @@ __global__ void __launch_bounds__(kBotThreads, 1) bottom_kernel(BottomArgs a) {
         }
         for (uint32_t b = tid; b < kSortBins + 1; b += kBotThreads) hist[b] = 0u;
         __syncthreads();
-        kmin = __reduce_min_sync(0xffffffffu, misc[8 + lane]);
-        kmax = __reduce_max_sync(0xffffffffu, misc[40 + lane]);
+        kmin = __reduce_min_sync(0xffffffffu, lane < kBotWarps ? misc[8 + lane] : 0xFFFFFFFFu);
+        kmax = __reduce_max_sync(0xffffffffu, lane < kBotWarps ? misc[40 + lane] : 0u);
         const float lo = __uint_as_float(ordered_to_float(kmin)), hi = __uint_as_float(ordered_to_float(kmax));
         const float scale = bin_scale(lo, hi, kSortBins);
         uint32_t bin[kBotItems], lr[kBotItems];

@@ -35,7 +35,10 @@ constexpr int kChunk = 2048; // points handled by one CTA of the streaming passe
 constexpr int kChunkThreads = 256;
 constexpr int kChunkItems = kChunk / kChunkThreads;
 constexpr int kChunkWarps = kChunkThreads / 32;
-constexpr int kBottomCap = 8192; // largest segment the bottom kernel splits in shared memory
+#ifndef NBK_BOTTOM_CAP
+#define NBK_BOTTOM_CAP 8192
+#endif
+constexpr int kBottomCap = NBK_BOTTOM_CAP; // largest segment the bottom kernel splits in shared memory
 constexpr int kSelectCap = 2048; // candidates sorted in shared memory by the select kernel
 
 // One segment of one level.  Level l has 2^l slots in heap order (children of s: 2s, 2s+1); a
