@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """GPU check of the select-and-partition build against the compiled reference (test tooling).
 
-    python scripts/build_check.py [--big]        # prints one JSON line per case
+    python tests/build_check_tool.py [--big]        # prints one JSON line per case
 
 Per case: node arrays (dim/left/right AND split: the split is the rank-median coordinate, unique
 even under ties) equal to the reference's; idx is a permutation and tuples are preserved; every
