@@ -1,0 +1,146 @@
+// Staged download of results into PAGEABLE host memory.
+//
+// The reference hands freshly allocated arrays to numpy (pybind.cpp:103-104,174-188); so does the
+// drop-in, and such memory is pageable and untouched.  A plain cudaMemcpy into it runs at ~20 GB/s and
+// takes one page fault per 4 KB on a single driver thread: 1.6 s for the 6.4 GB of a 10^8 x 8 result,
+// twenty times the kernel.  Here the device-to-host copy goes at full PCIe speed into a small ring of
+// pinned slots, and a few host threads move finished slots into the destination (first touch and
+// copy in parallel) while the GPU keeps computing the next slice.
+#pragma once
+
+#include <condition_variable>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+
+namespace nbk {
+
+class PinnedRing { // one per process, allocated on first use, handed to one staged call at a time
+  public:
+    static constexpr int kSlots = 8;
+    static constexpr size_t kSlotBytes = (size_t)32 << 20;
+    static PinnedRing *try_acquire() {
+        static PinnedRing ring;
+        if (!ring.lock_.try_lock()) return nullptr;
+        if (!ring.base_) {
+            void *p = nullptr;
+            if (cudaHostAlloc(&p, kSlots * kSlotBytes, cudaHostAllocPortable) != cudaSuccess) {
+                cudaGetLastError();
+                ring.lock_.unlock();
+                return nullptr;
+            }
+            ring.base_ = static_cast<char *>(p);
+        }
+        return &ring;
+    }
+    void release() { lock_.unlock(); }
+    char *slot(int i) const { return base_ + (size_t)i * kSlotBytes; }
+
+  private:
+    PinnedRing() = default;
+    std::mutex lock_;
+    char *base_ = nullptr;
+};
+
+class StagedDownload {
+  public:
+    StagedDownload(PinnedRing *ring, int device, int threads) : ring_(ring) {
+        for (int i = 0; i < PinnedRing::kSlots; ++i) {
+            NBK_CUDA(cudaEventCreateWithFlags(&events_[i], cudaEventDisableTiming));
+            free_[i] = true;
+        }
+        for (int t = 0; t < threads; ++t) workers_.emplace_back([this, device] { work(device); });
+    }
+    ~StagedDownload() {
+        finish();
+        for (auto &e : events_) cudaEventDestroy(e);
+        ring_->release();
+    }
+    // `bytes` from device memory (ready in `stream` order) to pageable `dst`; blocks only while the ring is full
+    void download(void *dst, const void *d_src, size_t bytes, cudaStream_t stream) {
+        for (size_t off = 0; off < bytes; off += PinnedRing::kSlotBytes) {
+            const size_t n = std::min(PinnedRing::kSlotBytes, bytes - off);
+            int slot = -1;
+            {
+                std::unique_lock<std::mutex> lock(mutex_);
+                cv_free_.wait(lock, [&] {
+                    for (int i = 0; i < PinnedRing::kSlots; ++i)
+                        if (free_[i]) {
+                            slot = i;
+                            return true;
+                        }
+                    return false;
+                });
+                free_[slot] = false;
+            }
+            NBK_CUDA(cudaMemcpyAsync(ring_->slot(slot), static_cast<const char *>(d_src) + off, n,
+                                     cudaMemcpyDeviceToHost, stream));
+            NBK_CUDA(cudaEventRecord(events_[slot], stream));
+            {
+                std::lock_guard<std::mutex> lock(mutex_);
+                tasks_.push_back(Task{slot, static_cast<char *>(dst) + off, n});
+            }
+            cv_task_.notify_one();
+        }
+    }
+    void finish() {
+        {
+            std::lock_guard<std::mutex> lock(mutex_);
+            if (done_) return;
+            done_ = true;
+        }
+        cv_task_.notify_all();
+        for (auto &w : workers_) w.join();
+        workers_.clear();
+    }
+
+  private:
+    struct Task {
+        int slot;
+        char *dst;
+        size_t bytes;
+    };
+    void work(int device) {
+        cudaSetDevice(device);
+        while (true) {
+            Task t;
+            {
+                std::unique_lock<std::mutex> lock(mutex_);
+                cv_task_.wait(lock, [&] { return done_ || !tasks_.empty(); });
+                if (tasks_.empty()) return; // done_ and drained
+                t = tasks_.front();
+                tasks_.pop_front();
+            }
+            cudaEventSynchronize(events_[t.slot]);
+            std::memcpy(t.dst, ring_->slot(t.slot), t.bytes);
+            {
+                std::lock_guard<std::mutex> lock(mutex_);
+                free_[t.slot] = true;
+            }
+            cv_free_.notify_one();
+        }
+    }
+    PinnedRing *ring_;
+    cudaEvent_t events_[PinnedRing::kSlots];
+    bool free_[PinnedRing::kSlots];
+    std::vector<std::thread> workers_;
+    std::mutex mutex_;
+    std::condition_variable cv_task_, cv_free_;
+    std::deque<Task> tasks_;
+    bool done_ = false;
+};
+
+inline bool is_pageable_host(const void *p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return attr.type == cudaMemoryTypeUnregistered;
+}
+
+} // namespace nbk

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "host_stage.cuh"
 #include "knn_query.cuh"
 #include "radix_sort.cuh"
 #include "tree_build.cuh"
@@ -666,6 +667,29 @@ int nbk_tree_query_ex(const nbk_tree *tree, const float *q_aos, uint64_t m, int 
                 cudaStreamDestroy(streams[s]);
             }
         };
+        // Results for pageable memory (fresh numpy arrays) go through a pinned ring and host threads
+        // (host_stage.cuh); pinned or registered destinations are written by the copy engine directly.
+        static const int host_threads = [] {
+            const char *v = std::getenv("NBK_HOST_THREADS");
+            int n = v ? std::atoi(v) : 0;
+            if (n <= 0) n = (int)std::min(8u, std::max(2u, std::thread::hardware_concurrency() / 2));
+            return n;
+        }();
+        std::unique_ptr<StagedDownload> staged;
+        if (m * (uint64_t)k * 8 >= (64u << 20) && is_pageable_host(out_dist) && is_pageable_host(out_idx)) {
+            if (PinnedRing *ring = PinnedRing::try_acquire())
+                staged = std::make_unique<StagedDownload>(ring, tree->device, host_threads);
+        }
+        auto download = [&](int s, uint64_t begin, uint64_t cnt) {
+            const uint64_t bytes = cnt * (uint64_t)k * 4;
+            if (staged) {
+                staged->download(out_dist + begin * k, d_d[s], bytes, streams[s]);
+                staged->download(out_idx + begin * k, d_i[s], bytes, streams[s]);
+            } else {
+                NBK_CUDA(cudaMemcpyAsync(out_dist + begin * k, d_d[s], bytes, cudaMemcpyDeviceToHost, streams[s]));
+                NBK_CUDA(cudaMemcpyAsync(out_idx + begin * k, d_i[s], bytes, cudaMemcpyDeviceToHost, streams[s]));
+            }
+        };
         try {
             for (int s = 0; s < nbuf; ++s) {
                 NBK_CUDA(cudaStreamCreateWithFlags(&streams[s], cudaStreamNonBlocking));
@@ -675,23 +699,31 @@ int nbk_tree_query_ex(const nbk_tree *tree, const float *q_aos, uint64_t m, int 
             }
             int s = 0;
             uint64_t step = std::min(slice, first_slice);
+            // the download of slice c is enqueued after the kernel of slice c+1, so that the device has
+            // work while this thread waits for ring slots
+            int pend_s = -1;
+            uint64_t pend_begin = 0, pend_cnt = 0;
             for (uint64_t begin = 0; begin < m; s = (s + 1) % nbuf) {
                 const uint64_t cnt = std::min(step, m - begin);
                 cudaStream_t st = streams[s];
                 NBK_CUDA(cudaMemcpyAsync(d_q[s], q_aos + begin * 3, cnt * 12, cudaMemcpyHostToDevice, st));
                 query_device(*tree, d_q[s], cnt, k, d_d[s], d_i[s], st, periodic, box_size);
-                NBK_CUDA(cudaMemcpyAsync(out_dist + begin * k, d_d[s], cnt * (uint64_t)k * 4,
-                                         cudaMemcpyDeviceToHost, st));
-                NBK_CUDA(cudaMemcpyAsync(out_idx + begin * k, d_i[s], cnt * (uint64_t)k * 4,
-                                         cudaMemcpyDeviceToHost, st));
+                if (pend_s >= 0) download(pend_s, pend_begin, pend_cnt);
+                pend_s = s;
+                pend_begin = begin;
+                pend_cnt = cnt;
                 begin += cnt;
                 step = std::min(slice, step * 2);
             }
+            if (pend_s >= 0) download(pend_s, pend_begin, pend_cnt);
+            if (staged) staged->finish();
             for (int t = 0; t < nbuf; ++t) NBK_CUDA(cudaStreamSynchronize(streams[t]));
         } catch (...) {
+            staged.reset();
             cleanup();
             throw;
         }
+        staged.reset();
         cleanup();
     });
 }

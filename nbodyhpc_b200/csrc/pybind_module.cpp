@@ -1,7 +1,10 @@
 // pybind11 module `_impl`: same class, argument names, defaults, property names and error
 // messages as the reference's kdtree/src/cpp/pybind.cpp:196-216, over the B200 C ABI.
+#include <cstdlib>
 #include <cstring>
 #include <optional>
+
+#include <sys/mman.h>
 
 #include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
@@ -13,6 +16,22 @@
 namespace py = pybind11;
 
 namespace {
+
+// Result arrays are allocated by the library and handed to numpy through a capsule, like the
+// reference's (pybind.cpp:103-104,174-188).  2 MB alignment + MADV_HUGEPAGE: a 10^8 x 8 result is
+// 3.2 GB per array, and filling it through 4 KB first-touch faults costs more than the query.
+template <typename T> py::array_t<T> make_result(py::ssize_t rows, py::ssize_t cols) {
+    constexpr size_t kHuge = (size_t)2 << 20;
+    const size_t bytes = (size_t)rows * (size_t)cols * sizeof(T);
+    const size_t alloc = (std::max<size_t>(bytes, 1) + kHuge - 1) / kHuge * kHuge;
+    void *p = std::aligned_alloc(bytes >= kHuge ? kHuge : 64, bytes >= kHuge ? alloc : (std::max<size_t>(bytes, 1) + 63) / 64 * 64);
+    if (!p) throw std::bad_alloc();
+#ifdef MADV_HUGEPAGE
+    if (bytes >= kHuge) madvise(p, alloc, MADV_HUGEPAGE);
+#endif
+    py::capsule owner(p, [](void *q) { std::free(q); });
+    return py::array_t<T>({rows, cols}, static_cast<T *>(p), owner);
+}
 
 void require_n_by_3(py::array_t<float> const &a) {
     // pybind.cpp:16-18 / :96-98
@@ -89,13 +108,14 @@ class PyKDTree : public wenda::kdtree::KDTree {
         if (k <= 0) throw std::runtime_error("k must be positive integer"); // pybind.cpp:92-94
         require_n_by_3(points);
         const uint64_t m = static_cast<uint64_t>(points.shape(0));
-        py::array_t<float> dist({(py::ssize_t)m, (py::ssize_t)k});
-        py::array_t<uint32_t> idx({(py::ssize_t)m, (py::ssize_t)k});
+        py::array_t<float> dist = make_result<float>((py::ssize_t)m, (py::ssize_t)k);
+        py::array_t<uint32_t> idx = make_result<uint32_t>((py::ssize_t)m, (py::ssize_t)k);
         const float *q = points.data();
         float *od = dist.mutable_data();
         uint32_t *oi = idx.mutable_data();
-        // Slices of 2^24 queries so that Ctrl-C is honoured between them (pybind.cpp:128-133).
-        const uint64_t slice = 1ull << 24;
+        // Pieces of 2^27 queries so that Ctrl-C is honoured between them (pybind.cpp:128-133); the
+        // library pipelines each piece in slices of its own.
+        const uint64_t slice = 1ull << 27;
         for (uint64_t begin = 0; begin < m; begin += slice) {
             uint64_t cnt = std::min(slice, m - begin);
             int status;

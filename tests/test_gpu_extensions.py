@@ -167,3 +167,26 @@ def test_kdtree_main_cli(gpu, tmp_path):
     assert out.returncode == 0 and out.stdout.startswith("Benchmarking kdtree with data from:"), out.stderr
     bad = subprocess.run([exe, "--no-such-flag"], capture_output=True, text=True, timeout=60)
     assert bad.returncode == 1 and "unknown option" in bad.stderr
+
+
+# ---- host pipeline ----------------------------------------------------------------------------------------
+def test_staged_download_into_pageable_memory_matches_pinned(gpu):
+    """Large results for ordinary numpy arrays go through the pinned ring + host threads
+    (host_stage.cuh); pinned destinations are written by the copy engine directly.  Same bytes."""
+    import torch
+
+    pts, q = philox(100_000, 42), philox(2_300_000, 43)
+    tree = gpu.Tree.build(pts, 64, 1.0)
+    k = 8
+    d_page, i_page = tree.query(q, k)  # 147 MB of results: staged
+    q_pin = torch.from_numpy(q).pin_memory()
+    d_pin = torch.empty((len(q), k), dtype=torch.float32).pin_memory()
+    i_pin = torch.empty((len(q), k), dtype=torch.int32).pin_memory()
+    tree.query_raw(q_pin.data_ptr(), len(q), k, d_pin.data_ptr(), i_pin.data_ptr())
+    assert np.array_equal(d_page, d_pin.numpy()) and np.array_equal(i_page, i_pin.numpy().view(np.uint32))
+    # and through the Python drop-in (library-allocated, huge-page advised result arrays)
+    from nbodyhpc_b200.kdtree import KDTree
+
+    d_py, i_py = KDTree(pts, leafsize=64, boxsize=1.0).query(q, k=k)
+    assert d_py.flags["C_CONTIGUOUS"] and d_py.flags["OWNDATA"] is False and d_py.base is not None
+    assert np.array_equal(d_py, d_page) and np.array_equal(i_py, i_page)
