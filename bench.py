@@ -194,6 +194,26 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Pins this process to the CPUs NVML names as local to GPU `index`, so that the pinned host buffers
+    of the end-to-end leg are first-touched on that GPU's NUMA node (with 8 ranks copying 7.6 GB per
+    step each, remote-node buffers halve the aggregate PCIe rate).  Best effort."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        cpus = [c for c in cpus if c < os.cpu_count()]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"cpus": f"{cpus[0]}-{cpus[-1]}", "count": len(cpus)}
+    except Exception as exc:  # pragma: no cover - depends on the box
+        return {"error": str(exc)[:80]}
+    return None
+
+
 # ---- the B200 arm -----------------------------------------------------------------------------------
 def run_b200_arm(args):
     import torch
@@ -207,8 +227,12 @@ def run_b200_arm(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # (N = 1 keeps all cores: the CPU-baseline leg of that run uses every host thread)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 and not os.environ.get("NBK_BENCH_NO_BIND") else None
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's version/debug banner goes to stderr
+        # stdout carries exactly one JSON line: no NCCL version banner (NCCL_DEBUG=VERSION prints it there)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     capi.lib()  # fail loudly if the extension is missing
@@ -308,7 +332,8 @@ def run_b200_arm(args):
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * m * e2e_steps / float(dt.item()), "unit": UNIT, "steps": e2e_steps,
                "h2d_bytes_per_step": m * 12, "d2h_bytes_per_step": m * k * 8,
-               "api": "nbk_tree_query (host pointers, pinned): 2^24-query slices, 3 streams, H2D/kernel/D2H overlapped"}
+               "api": "nbk_tree_query (host pointers, pinned): slices of 2^21..2^24 queries on 3 streams, "
+                      "H2D / kernel / D2H overlapped", "cpu_affinity": numa}
         same = bool(torch.equal(od_host[:100000], out_d[:100000].cpu()))
         e2e["matches_device_path"] = same
         del q_host, od_host, oi_host

@@ -408,3 +408,45 @@ def test_python_api_behaviour(gpu):
     assert np.array_equal(d3, d2)
     nodes = tree.nodes()
     assert len(nodes) == tree.size and nodes[0]["dim"] == 0
+
+
+@pytest.mark.parametrize("n", [0, 1, 7, 8, 9, 15, 16, 17, 24, 100])
+def test_tiny_trees(gpu, n):
+    """Point counts around the padding unit (8) and the minimum leaf (16): structure and answers."""
+    pts = philox(n, 31) if n else np.zeros((0, 3), np.float32)
+    tree = gpu.Tree.build(pts, 16)
+    nodes = tree.nodes()
+    x, y, z, idx = tree.points()
+    check_tree_invariants(nodes, x, y, z)
+    q = philox(20, 32)
+    k = 3
+    d, i = tree.query(q, k)
+    if n == 0:
+        # (the reference itself crashes when an empty tree is queried; the drop-in reports no neighbours)
+        assert tree.n == 0 and tree.size == 1
+        assert (d == SQRT_FLT_MAX).all() and (i == 0xFFFFFFFF).all()
+        return
+    ref = checker_tree(pts, 16, None)
+    assert tree.n == ref.n and tree.size == ref.size
+    d_ref, i_ref = ref.query(q, k)
+    assert np.array_equal(d.view(np.uint32), d_ref.view(np.uint32)) and np.array_equal(i, i_ref)
+
+
+def test_non_finite_coordinates_do_not_break_the_build(gpu):
+    """NaN / inf coordinates have no defined behaviour in the reference (comparisons are simply false);
+    here they must neither hang nor crash the selection, and the finite points stay searchable."""
+    rng = np.random.Generator(np.random.Philox(3))
+    pts = rng.random((50_000, 3), dtype=np.float32)
+    pts[::97, 0] = np.nan
+    pts[5::101, 1] = np.inf
+    pts[7::103, 2] = -np.inf
+    tree = gpu.Tree.build(pts, 32)
+    x, y, z, idx = tree.points()
+    assert np.array_equal(np.sort(idx), np.arange(tree.n, dtype=np.uint32))
+    q = rng.random((200, 3), dtype=np.float32)
+    d, i = tree.query(q, 4)
+    finite = np.isfinite(pts).all(1)
+    assert finite[i].all()
+    # the neighbours returned are real distances to finite points (no pruning guarantees with NaN splits)
+    recomputed = np.sqrt(((pts[i] - q[:, None, :]) ** 2).sum(-1, dtype=np.float32))
+    assert np.allclose(recomputed, d, rtol=1e-6)
