@@ -66,22 +66,43 @@ struct BlockCache {
         NBK_CUDA(cudaGetDevice(&dev));
         std::lock_guard<std::mutex> lock(mutex());
         auto &es = entries();
+        // best fit among this device's idle blocks that are not more than twice too big
+        Entry *best = nullptr;
         for (auto &e : es)
-            if (!e.busy && e.device == dev && e.bytes >= bytes && e.bytes / 2 <= bytes) {
-                e.busy = true;
-                return e.ptr;
-            }
-        // no fit: drop this device's idle blocks (they are the wrong size) and take a fresh one
-        for (size_t i = 0; i < es.size();) {
-            if (!es[i].busy && es[i].device == dev) {
-                cudaFree(es[i].ptr);
-                es.erase(es.begin() + i);
-            } else {
-                ++i;
+            if (!e.busy && e.device == dev && e.bytes >= bytes && e.bytes / 2 <= bytes && (!best || e.bytes < best->bytes))
+                best = &e;
+        if (best) {
+            best->busy = true;
+            return best->ptr;
+        }
+        // miss: if the cache is full of wrong-sized idle blocks, drop them, then take a fresh one
+        size_t idle = 0;
+        for (auto &e : es) idle += (!e.busy && e.device == dev) ? 1 : 0;
+        if (idle >= 4) {
+            for (size_t i = 0; i < es.size();) {
+                if (!es[i].busy && es[i].device == dev) {
+                    cudaFree(es[i].ptr);
+                    es.erase(es.begin() + i);
+                } else {
+                    ++i;
+                }
             }
         }
         void *p = nullptr;
-        NBK_CUDA(cudaMalloc(&p, bytes));
+        cudaError_t err = cudaMalloc(&p, bytes);
+        if (err != cudaSuccess) {
+            // out of memory with idle blocks cached: give them back and retry once
+            cudaGetLastError();
+            for (size_t i = 0; i < es.size();) {
+                if (!es[i].busy && es[i].device == dev) {
+                    cudaFree(es[i].ptr);
+                    es.erase(es.begin() + i);
+                } else {
+                    ++i;
+                }
+            }
+            NBK_CUDA(cudaMalloc(&p, bytes));
+        }
         es.push_back(Entry{p, bytes, dev, true});
         return p;
     }

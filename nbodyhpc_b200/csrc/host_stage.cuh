@@ -21,7 +21,8 @@ namespace nbk {
 
 class PinnedRing { // one per process, allocated on first use, handed to one staged call at a time
   public:
-    static constexpr int kSlots = 8;
+    static constexpr int kSlots = 12; // [0, kUploadSlots): uploads, the rest: downloads
+    static constexpr int kUploadSlots = 4;
     static constexpr size_t kSlotBytes = (size_t)32 << 20;
     static PinnedRing *try_acquire() {
         static PinnedRing ring;
@@ -51,7 +52,7 @@ class StagedDownload {
     StagedDownload(PinnedRing *ring, int device, int threads) : ring_(ring) {
         for (int i = 0; i < PinnedRing::kSlots; ++i) {
             NBK_CUDA(cudaEventCreateWithFlags(&events_[i], cudaEventDisableTiming));
-            free_[i] = true;
+            free_[i] = i >= PinnedRing::kUploadSlots; // the first slots belong to StagedUpload
         }
         for (int t = 0; t < threads; ++t) workers_.emplace_back([this, device] { work(device); });
     }
@@ -132,6 +133,90 @@ class StagedDownload {
     std::condition_variable cv_task_, cv_free_;
     std::deque<Task> tasks_;
     bool done_ = false;
+};
+
+// The other direction: pageable host memory -> device.  Host threads copy chunks into pinned slots
+// and issue the H2D copy of each; upload() returns when the data is on the device.
+class StagedUpload {
+  public:
+    StagedUpload(PinnedRing *ring, int device, int threads) : ring_(ring) {
+        for (int i = 0; i < PinnedRing::kUploadSlots; ++i) free_[i] = true;
+        for (int t = 0; t < threads; ++t) workers_.emplace_back([this, device] { work(device); });
+    }
+    ~StagedUpload() {
+        {
+            std::lock_guard<std::mutex> lock(mutex_);
+            done_ = true;
+        }
+        cv_task_.notify_all();
+        for (auto &w : workers_) w.join();
+    }
+    void upload(void *d_dst, const void *src, size_t bytes, cudaStream_t stream) {
+        for (size_t off = 0; off < bytes; off += PinnedRing::kSlotBytes) {
+            const size_t n = std::min(PinnedRing::kSlotBytes, bytes - off);
+            std::unique_lock<std::mutex> lock(mutex_);
+            int slot = -1;
+            cv_free_.wait(lock, [&] {
+                for (int i = 0; i < PinnedRing::kUploadSlots; ++i)
+                    if (free_[i]) {
+                        slot = i;
+                        return true;
+                    }
+                return false;
+            });
+            free_[slot] = false;
+            ++pending_;
+            tasks_.push_back(Task{slot, static_cast<char *>(d_dst) + off, static_cast<const char *>(src) + off, n, stream});
+            lock.unlock();
+            cv_task_.notify_one();
+        }
+        std::unique_lock<std::mutex> lock(mutex_);
+        cv_free_.wait(lock, [&] { return pending_ == 0; });
+        if (failed_) throw Error(NBK_ERR_CUDA, "staged upload failed");
+    }
+
+  private:
+    struct Task {
+        int slot;
+        char *d_dst;
+        const char *src;
+        size_t bytes;
+        cudaStream_t stream;
+    };
+    void work(int device) {
+        cudaSetDevice(device);
+        cudaEvent_t ev;
+        cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        while (true) {
+            Task t;
+            {
+                std::unique_lock<std::mutex> lock(mutex_);
+                cv_task_.wait(lock, [&] { return done_ || !tasks_.empty(); });
+                if (tasks_.empty()) break;
+                t = tasks_.front();
+                tasks_.pop_front();
+            }
+            std::memcpy(ring_->slot(t.slot), t.src, t.bytes);
+            bool ok = cudaMemcpyAsync(t.d_dst, ring_->slot(t.slot), t.bytes, cudaMemcpyHostToDevice, t.stream) == cudaSuccess;
+            ok = ok && cudaEventRecord(ev, t.stream) == cudaSuccess && cudaEventSynchronize(ev) == cudaSuccess;
+            {
+                std::lock_guard<std::mutex> lock(mutex_);
+                free_[t.slot] = true;
+                --pending_;
+                failed_ = failed_ || !ok;
+            }
+            cv_free_.notify_all();
+        }
+        cudaEventDestroy(ev);
+    }
+    PinnedRing *ring_;
+    bool free_[PinnedRing::kUploadSlots];
+    std::vector<std::thread> workers_;
+    std::mutex mutex_;
+    std::condition_variable cv_task_, cv_free_;
+    std::deque<Task> tasks_;
+    size_t pending_ = 0;
+    bool done_ = false, failed_ = false;
 };
 
 inline bool is_pageable_host(const void *p) {

@@ -476,18 +476,41 @@ nbk_tree *nbk_tree_build(const float *xyz_aos, uint64_t n, int leaf_size, int bl
         require_sm100(device);
         DeviceGuard guard(device);
         cudaStream_t stream = nullptr; // legacy default stream
-        float *d_aos = nullptr;
-        NBK_CUDA(cudaMalloc(&d_aos, std::max<uint64_t>(n, 1) * 12));
+        const auto t0 = std::chrono::steady_clock::now();
+        auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+        const char *tv = std::getenv("NBK_BUILD_TRACE");
+        const bool trace = tv && tv[0] == '1';
         std::unique_ptr<nbk_tree> tree;
-        try {
-            NBK_CUDA(cudaMemcpyAsync(d_aos, xyz_aos, n * 12, cudaMemcpyHostToDevice, stream));
-            tree = build_from_device_aos(d_aos, n, leaf_size, block_size, periodic, box_size, device,
-                                         stream);
-        } catch (...) {
-            cudaFree(d_aos);
-            throw;
+        {
+            // the staging copy of the caller's points comes from the block cache too (kept between builds)
+            Scratch staging(stream);
+            staging.reserve(Scratch::padded(std::max<uint64_t>(n, 1) * 12));
+            float *d_aos = staging.get<float>(std::max<uint64_t>(n, 1) * 3);
+            const double t_alloc = since();
+            {
+                PinnedRing *ring = (n * 12ull >= (32u << 20) && is_pageable_host(xyz_aos)) ? PinnedRing::try_acquire() : nullptr;
+                if (ring) {
+                    struct Release {
+                        PinnedRing *r;
+                        ~Release() { r->release(); }
+                    } release{ring};
+                    int dev = 0;
+                    NBK_CUDA(cudaGetDevice(&dev));
+                    static const int threads = (int)std::min(8u, std::max(2u, std::thread::hardware_concurrency() / 2));
+                    StagedUpload up(ring, dev, threads);
+                    up.upload(d_aos, xyz_aos, n * 12, stream);
+                } else {
+                    NBK_CUDA(cudaMemcpyAsync(d_aos, xyz_aos, n * 12, cudaMemcpyHostToDevice, stream));
+                    NBK_CUDA(cudaStreamSynchronize(stream));
+                }
+            }
+            const double t_copy = since();
+            tree = build_from_device_aos(d_aos, n, leaf_size, block_size, periodic, box_size, device, stream);
+            if (trace)
+                fprintf(stderr, "[nbk build] host entry: staging block %.3f ms, upload of %.1f MB %.3f ms, build %.3f ms\n",
+                        t_alloc, n * 12 / 1e6, t_copy - t_alloc, since() - t_copy);
         }
-        cudaFree(d_aos);
+        if (trace) fprintf(stderr, "[nbk build] host entry total %.3f ms\n", since());
         out = tree.release();
     });
     if (status) *status = st;
@@ -676,10 +699,23 @@ int nbk_tree_query_ex(const nbk_tree *tree, const float *q_aos, uint64_t m, int 
             return n;
         }();
         std::unique_ptr<StagedDownload> staged;
+        PinnedRing *staged_ring = nullptr;
         if (m * (uint64_t)k * 8 >= (64u << 20) && is_pageable_host(out_dist) && is_pageable_host(out_idx)) {
-            if (PinnedRing *ring = PinnedRing::try_acquire())
-                staged = std::make_unique<StagedDownload>(ring, tree->device, host_threads);
+            if ((staged_ring = PinnedRing::try_acquire()))
+                staged = std::make_unique<StagedDownload>(staged_ring, tree->device, host_threads);
         }
+        std::unique_ptr<StagedUpload> uploader;
+        PinnedRing *upload_ring = nullptr;
+        if (m * 12ull >= (32u << 20) && is_pageable_host(q_aos)) {
+            // shares the ring of the staged download if there is one, otherwise takes it for itself
+            if (staged) upload_ring = staged_ring;
+            else upload_ring = PinnedRing::try_acquire();
+            if (upload_ring) uploader = std::make_unique<StagedUpload>(upload_ring, tree->device, std::max(2, host_threads / 2));
+        }
+        struct RingRelease {
+            PinnedRing *ring;
+            ~RingRelease() { if (ring) ring->release(); }
+        } upload_ring_release{staged ? nullptr : upload_ring};
         auto download = [&](int s, uint64_t begin, uint64_t cnt) {
             const uint64_t bytes = cnt * (uint64_t)k * 4;
             if (staged) {
@@ -706,7 +742,8 @@ int nbk_tree_query_ex(const nbk_tree *tree, const float *q_aos, uint64_t m, int 
             for (uint64_t begin = 0; begin < m; s = (s + 1) % nbuf) {
                 const uint64_t cnt = std::min(step, m - begin);
                 cudaStream_t st = streams[s];
-                NBK_CUDA(cudaMemcpyAsync(d_q[s], q_aos + begin * 3, cnt * 12, cudaMemcpyHostToDevice, st));
+                if (uploader) uploader->upload(d_q[s], q_aos + begin * 3, cnt * 12, st);
+                else NBK_CUDA(cudaMemcpyAsync(d_q[s], q_aos + begin * 3, cnt * 12, cudaMemcpyHostToDevice, st));
                 query_device(*tree, d_q[s], cnt, k, d_d[s], d_i[s], st, periodic, box_size);
                 if (pend_s >= 0) download(pend_s, pend_begin, pend_cnt);
                 pend_s = s;
@@ -719,10 +756,12 @@ int nbk_tree_query_ex(const nbk_tree *tree, const float *q_aos, uint64_t m, int 
             if (staged) staged->finish();
             for (int t = 0; t < nbuf; ++t) NBK_CUDA(cudaStreamSynchronize(streams[t]));
         } catch (...) {
+            uploader.reset();
             staged.reset();
             cleanup();
             throw;
         }
+        uploader.reset();
         staged.reset();
         cleanup();
     });
