@@ -226,7 +226,7 @@ std::unique_ptr<nbk_tree> build_from_device_aos(const float *d_aos, uint64_t n, 
         const uint32_t init[8] = {0u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u, 0u};
         NBK_CUDA(cudaMemcpyAsync(aux, init, sizeof init, cudaMemcpyHostToDevice, stream));
         if (n_padded) {
-            ingest_aos_kernel<<<(unsigned)std::min<uint64_t>(div_up(n_padded, 256), 148 * 16), 256, 0, stream>>>(
+            ingest_aos_kernel<<<(unsigned)std::min<uint64_t>(div_up(n_padded, 1024), 148 * 8), 256, 0, stream>>>(
                 d_aos, n, n_padded, x0, y0, z0, perm, periodic, box_size, aux, aux + 1);
             NBK_LAUNCHED();
         }

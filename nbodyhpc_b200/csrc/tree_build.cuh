@@ -103,39 +103,47 @@ ingest_aos_kernel(const float *__restrict__ aos, uint64_t n, uint64_t n_padded,
                   float *__restrict__ x, float *__restrict__ y, float *__restrict__ z,
                   uint32_t *__restrict__ perm, int periodic, float box, uint32_t *flags,
                   uint32_t *bounds6) {
-    __shared__ float tile[256 * 3];
+    constexpr int kTile = 1024; // points per iteration: 12 independent loads per thread in flight
+    __shared__ float tile[kTile * 3];
     uint32_t lo[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, hi[3] = {0u, 0u, 0u};
     bool bad = false;
-    for (uint64_t base = (uint64_t)blockIdx.x * 256; base < n_padded; base += (uint64_t)gridDim.x * 256) {
-        const uint64_t in_tile = n > base ? (n - base < 256 ? n - base : 256) : 0;
-        for (uint32_t j = threadIdx.x; j < in_tile * 3; j += 256) tile[j] = aos[base * 3 + j];
-        __syncthreads();
-        const uint64_t i = base + threadIdx.x;
-        float px = FLT_MAX, py = FLT_MAX, pz = FLT_MAX;
-        const bool real = i < n;
-        if (real) {
-            px = tile[threadIdx.x * 3];
-            py = tile[threadIdx.x * 3 + 1];
-            pz = tile[threadIdx.x * 3 + 2];
-        }
-        __syncthreads();
-        if (i < n_padded) {
-            x[i] = px;
-            y[i] = py;
-            z[i] = pz;
-            perm[i] = (uint32_t)i;
-        }
-        bad = bad || (real && periodic &&
-                      !(px >= 0.0f && px <= box && py >= 0.0f && py <= box && pz >= 0.0f && pz <= box));
-        if (real) {
-            const float p[3] = {px, py, pz};
+    for (uint64_t base = (uint64_t)blockIdx.x * kTile; base < n_padded; base += (uint64_t)gridDim.x * kTile) {
+        const uint64_t in_tile = n > base ? (n - base < (uint64_t)kTile ? n - base : (uint64_t)kTile) : 0;
+        float v[12];
 #pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                const uint32_t o = float_to_ordered(__float_as_uint(p[d]));
-                lo[d] = min(lo[d], o);
-                hi[d] = max(hi[d], o);
+        for (int j = 0; j < 12; ++j) {
+            const uint32_t f = j * 256 + threadIdx.x;
+            v[j] = f < in_tile * 3 ? __ldcs(aos + base * 3 + f) : FLT_MAX;
+        }
+#pragma unroll
+        for (int j = 0; j < 12; ++j) tile[j * 256 + threadIdx.x] = v[j];
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t p = j * 256 + threadIdx.x;
+            const uint64_t i = base + p;
+            const bool real = i < n;
+            // padding points are (FLT_MAX, FLT_MAX, FLT_MAX) (pybind.cpp:23-33): the tile was filled with it
+            const float px = tile[p * 3], py = tile[p * 3 + 1], pz = tile[p * 3 + 2];
+            if (i < n_padded) {
+                x[i] = px;
+                y[i] = py;
+                z[i] = pz;
+                perm[i] = (uint32_t)i;
+            }
+            bad = bad || (real && periodic &&
+                          !(px >= 0.0f && px <= box && py >= 0.0f && py <= box && pz >= 0.0f && pz <= box));
+            if (real) {
+                const float c[3] = {px, py, pz};
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    const uint32_t o = float_to_ordered(__float_as_uint(c[d]));
+                    lo[d] = min(lo[d], o);
+                    hi[d] = max(hi[d], o);
+                }
             }
         }
+        __syncthreads();
     }
     if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flags, 1u);
     block_bounds(lo, hi, bounds6);

@@ -389,10 +389,15 @@ select_kernel(const Seg *__restrict__ segs, const Sel *__restrict__ sel,
     unsigned long long base = 0ull, span = ~0ull;
     if (c > (uint32_t)kSelectCap) {
         unsigned long long mn = ~0ull, mx = 0ull;
-        for (uint32_t i = tid; i < c_all; i += bd) {
-            const unsigned long long v = cp[i];
-            mn = v < mn ? v : mn;
-            mx = v > mx ? v : mx;
+        for (uint32_t i0 = tid; i0 < c_all; i0 += 4u * bd) {
+            unsigned long long v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = i0 + u * bd < c_all ? cp[i0 + u * bd] : cp[i0];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                mn = v[u] < mn ? v[u] : mn;
+                mx = v[u] > mx ? v[u] : mx;
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -420,9 +425,14 @@ select_kernel(const Seg *__restrict__ segs, const Sel *__restrict__ sel,
             const int shift = bits > 8 ? bits - 8 : 0;
             for (int b = tid; b < 256; b += bd) sh[b] = 0;
             __syncthreads();
-            for (uint32_t i = tid; i < c_all; i += bd) {
-                const unsigned long long v = cp[i];
-                if (v >= base && v - base <= span) atomicAdd(&sh[(uint32_t)((v - base) >> shift)], 1u);
+            for (uint32_t i0 = tid; i0 < c_all; i0 += 4u * bd) {
+                unsigned long long v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = i0 + u * bd < c_all ? cp[i0 + u * bd] : ~0ull;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (i0 + u * bd < c_all && v[u] >= base && v[u] - base <= span)
+                        atomicAdd(&sh[(uint32_t)((v[u] - base) >> shift)], 1u);
             }
             __syncthreads();
             if (tid == 0) {
@@ -592,10 +602,10 @@ partition_kernel(Columns in, Columns out, const Seg *__restrict__ segs,
             const uint32_t rk = rank[r] & 0x7FFFFFFFu;
             const uint64_t dst = gbase + (left ? s_base[0] + cntL[r * kChunkWarps + warp] + rk
                                                : right_start + s_base[1] + cntR[r * kChunkWarps + warp] + rk);
-            out.x[dst] = px[r];
-            out.y[dst] = py[r];
-            out.z[dst] = pz[r];
-            out.id[dst] = pid[r];
+            __stcs(out.x + dst, px[r]); // written once, read once by the next pass: keep it out of the way
+            __stcs(out.y + dst, py[r]);
+            __stcs(out.z + dst, pz[r]);
+            __stcs(out.id + dst, pid[r]);
         }
     }
     if (FUSE_HIST) {
