@@ -138,9 +138,19 @@ struct Scratch {
     explicit Scratch(cudaStream_t s) : stream(s) {}
     Scratch(Scratch const &) = delete;
     static uint64_t padded(uint64_t bytes) { return (bytes + 255) / 256 * 256; }
+    static constexpr uint64_t kCacheFrom = 64ull << 20; // smaller blocks: the pool is quick and exact
+    bool block_cached = false;
     void reserve(uint64_t bytes) {
         if (block || bytes == 0) return;
-        block = static_cast<char *>(BlockCache::acquire(bytes));
+        if (bytes >= kCacheFrom) {
+            block = static_cast<char *>(BlockCache::acquire(bytes));
+            block_cached = true;
+        } else {
+            void *p = nullptr;
+            NBK_CUDA(cudaMallocAsync(&p, bytes, stream));
+            ptrs[count++] = p;
+            block = static_cast<char *>(p);
+        }
         block_bytes = bytes;
         total_bytes += bytes;
     }
@@ -161,7 +171,7 @@ struct Scratch {
     }
     ~Scratch() {
         for (int i = count - 1; i >= 0; --i) cudaFreeAsync(ptrs[i], stream);
-        if (block) {
+        if (block && block_cached) {
             cudaStreamSynchronize(stream);
             BlockCache::release(block);
         }

@@ -595,10 +595,21 @@ __global__ void __launch_bounds__(kBotThreads, kBotThreads <= 512 ? 2 : 1) botto
         for (int r = 0; r < kBotItems; ++r)
             if (r * kBotThreads + tid < n) put_tile(stage, pp[r], px[r], py[r], pz[r], pi[r]);
     }
+    // The staged tiles are one contiguous run of n x 16 bytes in shared memory and in the arena: one TMA
+    // bulk store (cp.async.bulk, shared -> global) issued by a single thread moves it; the generic-proxy
+    // writes above are made visible to the async proxy first.
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    float4 *dst = reinterpret_cast<float4 *>(a.tiles + (gbase >> 3) * 32);
-    const float4 *src = reinterpret_cast<const float4 *>(stage);
-    for (uint32_t i = tid; i < n; i += kBotThreads) dst[i] = src[i]; // n points = n float4
+    if (tid == 0) {
+        float *dst = a.tiles + (gbase >> 3) * 32;
+        const uint32_t src = (uint32_t)__cvta_generic_to_shared(stage);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
+                     "cp.async.bulk.commit_group;\n"
+                     "cp.async.bulk.wait_group.read 0;\n"
+                     :
+                     : "l"(dst), "r"(src), "r"(n * 16u)
+                     : "memory");
+    }
 }
 
 } // namespace td
