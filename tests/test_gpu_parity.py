@@ -450,3 +450,40 @@ def test_non_finite_coordinates_do_not_break_the_build(gpu):
     # the neighbours returned are real distances to finite points (no pruning guarantees with NaN splits)
     recomputed = np.sqrt(((pts[i] - q[:, None, :]) ** 2).sum(-1, dtype=np.float32))
     assert np.allclose(recomputed, d, rtol=1e-6)
+
+
+def test_sort_build_cross_check(gpu, tmp_path):
+    """NBK_BUILD=sort (one segmented radix sort per level, the first implementation) and the default
+    select-and-partition build are independent code paths: where no coordinate repeats they must give
+    the same node array and the same point set in every leaf."""
+    import os
+    import subprocess
+    import sys
+
+    n = 200_003
+    rng = np.random.Generator(np.random.Philox(17))
+    # every coordinate value occurs once per axis
+    pts = np.stack([(rng.permutation(n) + 0.5) / n for _ in range(3)], 1).astype(np.float32)
+    assert all(len(np.unique(pts[:, a])) == n for a in range(3))
+    np.save(tmp_path / "pts.npy", pts)
+    script = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "from nbodyhpc_b200 import capi\n"
+        "t = capi.Tree.build(np.load(%r), 32)\n"
+        "x, y, z, idx = t.points()\n"
+        "np.savez(%r, nodes=t.nodes().view(np.uint8), idx=idx)\n"
+    )
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = {}
+    for mode in ("select", "sort"):
+        dst = str(tmp_path / f"{mode}.npz")
+        env = dict(os.environ, NBK_BUILD=mode)
+        subprocess.run([sys.executable, "-c", script % (root, str(tmp_path / "pts.npy"), dst)], check=True, env=env,
+                       timeout=120)
+        out[mode] = np.load(dst)
+    assert np.array_equal(out["select"]["nodes"], out["sort"]["nodes"])
+    from nbodyhpc_b200.capi import NODE_DTYPE
+
+    nodes = out["select"]["nodes"].view(NODE_DTYPE)
+    a, b = leaf_sets(nodes, out["select"]["idx"]), leaf_sets(nodes, out["sort"]["idx"])
+    assert a.keys() == b.keys() and all(np.array_equal(a[key], b[key]) for key in a)
