@@ -581,10 +581,18 @@ int nbk_plan_topology(uint64_t n_points, int leaf_size, int block_size, nbk_node
         check_build_args(n_points, block_size, false);
         uint64_t n_padded = div_up(n_points, block_size) * block_size;
         check_build_args(n_padded, block_size, false);
-        TopologyPlan plan = plan_topology(n_padded, leaf_size, block_size);
-        if (n_nodes) *n_nodes = plan.nodes.size();
-        if (n_levels) *n_levels = (int)plan.levels.size();
-        if (nodes) std::copy(plan.nodes.begin(), plan.nodes.end(), nodes);
+        // the memoised count rules the build uses (no O(n_nodes) work) ...
+        td::TopPlan top = td::plan_top(n_padded, leaf_size, block_size);
+        if (n_nodes) *n_nodes = top.n_nodes;
+        if (n_levels) *n_levels = top.n_levels;
+        if (nodes) {
+            // ... and the explicit recursion (kdtree_impl.hpp:98-157) when the records are wanted; the two
+            // must agree
+            TopologyPlan plan = plan_topology(n_padded, leaf_size, block_size);
+            if (plan.nodes.size() != top.n_nodes || (int)plan.levels.size() != top.n_levels)
+                throw Error(NBK_ERR_INVALID, "internal error: topology plans disagree");
+            std::copy(plan.nodes.begin(), plan.nodes.end(), nodes);
+        }
     });
 }
 
