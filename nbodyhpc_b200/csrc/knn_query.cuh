@@ -43,7 +43,10 @@ __device__ __forceinline__ float tile_coord(const float4 *tiles, uint32_t p, int
     return reinterpret_cast<const float *>(tiles)[(uint64_t)(p >> 3) * 32 + axis * 8 + (p & 7)];
 }
 
-constexpr int kQueryThreads = 128;
+#ifndef NBK_QUERY_THREADS
+#define NBK_QUERY_THREADS 128
+#endif
+constexpr int kQueryThreads = NBK_QUERY_THREADS;
 constexpr int kQueryWarps = kQueryThreads / 32;
 
 // ---- Morton ordering of the queries --------------------------------------------------------------
@@ -380,7 +383,11 @@ __device__ __forceinline__ void cdf_accumulate(CdfArgs const &c, int j, uint32_t
 }
 
 template <typename Top, bool PERIODIC, bool IMAGES>
-__global__ void __launch_bounds__(kQueryThreads, (IMAGES || Top::kShared) ? 1 : NBK_LANE_MIN_BLOCKS)
+// resident CTAs per SM the register allocation aims for: 9 (56 registers) measured best for K = 8
+// (8: 81.2, 9: 78.8, 10: 78.8 ms per 10^8 queries; 64- and 256-thread CTAs: 79.1 / 81.6); the short
+// lists of K <= 4 fit 48 registers (57.1 -> 54.7 ms at k = 4)
+__global__ void __launch_bounds__(kQueryThreads, (IMAGES || Top::kShared) ? 1
+                                                 : (Top::kSize <= 4 ? NBK_LANE_MIN_BLOCKS + 1 : NBK_LANE_MIN_BLOCKS))
 knn_lane_kernel(QueryTree t, const float *__restrict__ q_aos, const uint32_t *__restrict__ order,
                 uint64_t m, int k_out, float *__restrict__ out_d, uint32_t *__restrict__ out_i,
                 DeferList defer, CdfArgs cdf) {
