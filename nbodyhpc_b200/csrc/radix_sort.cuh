@@ -173,7 +173,15 @@ scatter_kernel(const KeyT *__restrict__ kin, const uint32_t *__restrict__ vin,
         uint64_t i = warp_base + it * 32 + lane;
         bool ok = i < n;
         uint32_t d = ok ? ((uint32_t)(k[it] >> shift) & (kRadix - 1)) : 0xFFFFu;
-        uint32_t peers = __match_any_sync(0xffffffffu, d);
+        // lanes with the same digit: one ballot per bit (MATCH.ANY serialises over the distinct values of
+        // the warp and is several times slower for 8-bit digits)
+        uint32_t peers = __ballot_sync(0xffffffffu, ok);
+#pragma unroll
+        for (int b = 0; b < kRadixBits; ++b) {
+            const bool bit = (d >> b) & 1u;
+            const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+            peers &= bit ? bal : ~bal;
+        }
         uint32_t pre = ok ? wh[d] : 0u;
         __syncwarp();
         uint32_t rank = __popc(peers & lt_mask);
