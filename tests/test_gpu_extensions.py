@@ -190,3 +190,17 @@ def test_staged_download_into_pageable_memory_matches_pinned(gpu):
     d_py, i_py = KDTree(pts, leafsize=64, boxsize=1.0).query(q, k=k)
     assert d_py.flags["C_CONTIGUOUS"] and d_py.flags["OWNDATA"] is False and d_py.base is not None
     assert np.array_equal(d_py, d_page) and np.array_equal(i_py, i_page)
+
+
+# ---- the C++ drop-in, exercised like the reference's own gtest suite ------------------------------------------
+def test_cpp_dropin_replays_reference_cpp_tests(gpu, tmp_path):
+    """tests/cpp/test_kdtree_dropin.cpp = kdtree/src/cpp/tests/test.cpp:43-114 against
+    include/kdtree/*.hpp (wenda::kdtree::KDTree over the C ABI): built and run here."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "nbodyhpc_b200", "lib")
+    exe = str(tmp_path / "test_kdtree_dropin")
+    subprocess.run(["g++", "-O2", "-std=c++20", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "tests", "cpp", "test_kdtree_dropin.cpp"), "-o", exe, "-L", libdir, "-lnbk",
+                    f"-Wl,-rpath,{libdir}"], check=True, timeout=300)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "all checks passed" in out.stdout, out.stdout + out.stderr
