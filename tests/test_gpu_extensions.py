@@ -204,3 +204,25 @@ def test_cpp_dropin_replays_reference_cpp_tests(gpu, tmp_path):
                     f"-Wl,-rpath,{libdir}"], check=True, timeout=300)
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "all checks passed" in out.stdout, out.stdout + out.stderr
+
+
+def test_concurrent_queries_on_one_tree(gpu):
+    """A const KDTree is safe for concurrent find_closest in the reference (kdtree.hpp:207-210, the pybind
+    thread pool relies on it); the same must hold for concurrent batched queries on one device tree."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    pts = philox(300_000, 42)
+    tree = gpu.Tree.build(pts, 64, 1.0)
+    batches = [philox(400_000 + 1000 * j, 50 + j) for j in range(6)]
+    ks = [1, 8, 16, 8, 3, 32]
+    serial = [tree.query(q, k) for q, k in zip(batches, ks)]
+    with ThreadPoolExecutor(max_workers=6) as pool:
+        parallel = list(pool.map(lambda a: tree.query(a[0], a[1]), zip(batches, ks)))
+    for (d0, i0), (d1, i1) in zip(serial, parallel):
+        assert np.array_equal(d0, d1) and np.array_equal(i0, i1)
+    # builds may run concurrently with queries too
+    with ThreadPoolExecutor(max_workers=3) as pool:
+        f_build = pool.submit(lambda: gpu.Tree.build(philox(200_000, 7), 32))
+        f_query = pool.submit(lambda: tree.query(batches[1], 8))
+        other, (d, i) = f_build.result(), f_query.result()
+    assert np.array_equal(d, serial[1][0]) and other.size > 1
