@@ -87,3 +87,27 @@ def replicate_tree(tree: Optional[capi.Tree], src: int = 0, group=None, device: 
         tree = capi.Tree.alloc_replica(meta, device)
     dist.broadcast(arena_tensor(tree), src=src, group=group)
     return tree
+
+
+def reduce_cdf_counts(local_counts: np.ndarray, group=None, device: str = "cpu") -> np.ndarray:
+    """Sum of the per-rank kNN-CDF histograms (the one step of the sharded path that has an exchange:
+    every rank histograms the k-th neighbour distances of ITS queries, the totals are one all-reduce of
+    ``len(ks) * n_bins`` integers).  Works on any backend (CPU tensors for gloo, device for nccl)."""
+    import torch
+    import torch.distributed as dist
+
+    t = torch.from_numpy(np.ascontiguousarray(local_counts).astype(np.int64)).to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy().astype(np.uint64)
+
+
+def knn_cdf_sharded(tree: capi.Tree, queries: np.ndarray, ks, edges, group=None) -> np.ndarray:
+    """Fused kNN-CDF of a query set that is sharded over the ranks: ``queries`` is the WHOLE set (every
+    rank holds it, as with the reference's thread pool), each rank answers its contiguous chunk on its
+    own replica, and the histograms are summed.  Every rank returns the total."""
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    b, e = shard_range(len(queries), rank, world)
+    local = tree.knn_cdf(queries[b:e], ks, edges)
+    return reduce_cdf_counts(local, group, device=f"cuda:{tree.device}" if dist.get_backend(group) == "nccl" else "cpu")

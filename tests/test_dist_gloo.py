@@ -44,7 +44,13 @@ def _worker(rank, world, port, out_dir):
     tree = Oracle.Tree(pts, 64, 2.0)
     b, e = shard_range(len(q), rank, world)
     d, i = tree.query(q[b:e], 4)
-    np.savez(os.path.join(out_dir, f"shard{rank}.npz"), d=d, i=i, b=b, e=e)
+    # the sharded kNN-CDF: per-rank histograms of the 4th-neighbour distance, summed by one all-reduce
+    from nbodyhpc_b200.dist import reduce_cdf_counts
+
+    edges = np.linspace(0.0, 0.5, 11).astype(np.float32)
+    local = np.stack([np.histogram(d[:, k - 1], bins=edges)[0] for k in (1, 4)]).astype(np.uint64)
+    total = reduce_cdf_counts(local)
+    np.savez(os.path.join(out_dir, f"shard{rank}.npz"), d=d, i=i, b=b, e=e, cdf=total)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -59,3 +65,7 @@ def test_two_rank_sharded_query_equals_single_process(tmp_path):
     d = np.concatenate([s["d"] for s in shards])
     i = np.concatenate([s["i"] for s in shards])
     assert np.array_equal(d.view(np.uint32), d_full.view(np.uint32)) and np.array_equal(i, i_full)
+    edges = np.linspace(0.0, 0.5, 11).astype(np.float32)
+    expect = np.stack([np.histogram(d_full[:, k - 1], bins=edges)[0] for k in (1, 4)]).astype(np.uint64)
+    for s in shards:  # every rank holds the total
+        assert np.array_equal(s["cdf"], expect)

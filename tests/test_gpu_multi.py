@@ -32,7 +32,10 @@ def _worker(rank, world, port, out_dir):
     tree = replicate_tree(tree, src=0, device=rank)
     b, e = shard_range(len(q), rank, world)
     d, i = tree.query(q[b:e], 8)
-    np.savez(os.path.join(out_dir, f"shard{rank}.npz"), d=d, i=i, nodes=tree.nodes().view(np.uint8))
+    from nbodyhpc_b200.dist import knn_cdf_sharded
+
+    cdf = knn_cdf_sharded(tree, q, [1, 8], np.linspace(0.0, 0.1, 21).astype(np.float32))
+    np.savez(os.path.join(out_dir, f"shard{rank}.npz"), d=d, i=i, nodes=tree.nodes().view(np.uint8), cdf=cdf)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -54,6 +57,10 @@ def test_replica_is_byte_identical_and_shards_compose(gpu, tmp_path):
     d = np.concatenate([s["d"] for s in shards])
     i = np.concatenate([s["i"] for s in shards])
     assert np.array_equal(d.view(np.uint32), d_full.view(np.uint32)) and np.array_equal(i, i_full)
+    edges = np.linspace(0.0, 0.1, 21).astype(np.float32)
+    expect = np.stack([np.histogram(d_full[:, k - 1], bins=edges)[0] for k in (1, 8)]).astype(np.uint64)
+    for s in shards:
+        assert np.array_equal(s["cdf"], expect)
 
 
 def test_in_process_replicas_from_python(gpu):
