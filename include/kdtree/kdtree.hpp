@@ -25,12 +25,8 @@
 #include <vector>
 
 #include "../nbk.h"
+#include "../span.hpp" // tcb::span, the name the reference's signatures use (kdtree.hpp:11)
 #include "position_array.hpp"
-
-// The reference's signatures use tcb::span (a vendored C++11 span); C++20 has the real one.
-namespace tcb {
-using std::span;
-}
 
 namespace wenda {
 namespace kdtree {

@@ -77,5 +77,24 @@ inline std::vector<std::array<float, 3>> fill_random_positions(uint32_t n, unsig
     return positions;
 }
 
+//! kdtree.cpp:64-90 (declared kdtree_utils.hpp:117-118): AoS positions -> SoA columns with indices
+//! 0..n-1; if block_size > 0 the array is padded to a multiple of it with max() positions (the padding
+//! points carry the indices n.. like every other row).  Defined inline here: the reference compiles it
+//! into its library, the drop-in is header-only above the C ABI.
+inline PositionAndIndexArray<3, float, uint32_t>
+make_position_and_indices(tcb::span<const std::array<float, 3>> const &positions, int block_size = -1) {
+    const size_t n = positions.size();
+    const size_t block = block_size > 0 ? static_cast<size_t>(block_size) : 1;
+    const size_t padded = (n + block - 1) / block * block;
+    PositionAndIndexArray<3, float, uint32_t> out(padded);
+    for (size_t dim = 0; dim < 3; ++dim) {
+        float *column = out.positions_[dim];
+        for (size_t i = 0; i < n; ++i) column[i] = positions[i][dim];
+        std::fill(column + n, column + padded, std::numeric_limits<float>::max());
+    }
+    std::iota(out.indices_.begin(), out.indices_.end(), 0u);
+    return out;
+}
+
 } // namespace kdtree
 } // namespace wenda

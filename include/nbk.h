@@ -54,7 +54,7 @@ typedef struct nbk_tree_meta {
     uint64_t n_points;    /* points supplied by the caller                                  */
     uint64_t n_padded;    /* rounded up to a multiple of block_size (pybind.cpp:23)         */
     uint64_t n_nodes;
-    uint64_t arena_bytes; /* size of the packed device arena [nodes | x | y | z | idx]      */
+    uint64_t arena_bytes; /* size of the packed device arena [nodes | 128-byte point tiles]  */
     int32_t leaf_size;    /* as given by the caller (effective = max(leaf_size, 2*block))   */
     int32_t block_size;
     int32_t periodic;
@@ -133,8 +133,32 @@ NBK_API int nbk_tree_query_device(const nbk_tree *tree, const float *d_q_aos, ui
 NBK_API int nbk_tree_query_ex(const nbk_tree *tree, const float *q_aos, uint64_t m, int k,
                               int periodic, float box_size, float *out_dist, uint32_t *out_idx);
 
+/* flags of the entry points below */
+enum { NBK_QUERY_SQUARED = 1 /* rows hold the squared distances d2 the search ranks by (bit-exact to the
+                                reference's L2Distance / L2PeriodicDistance value BEFORE postprocess(),
+                                kdtree.hpp:22-31,71-84) instead of sqrt(d2) */ };
+
+/* nbk_tree_query_ex plus `flags` (NBK_QUERY_*). */
+NBK_API int nbk_tree_query_ex2(const nbk_tree *tree, const float *q_aos, uint64_t m, int k,
+                               int periodic, float box_size, int flags, float *out_dist, uint32_t *out_idx);
+
+/* nbk_tree_query_device plus the per-call metric and `flags`. */
+NBK_API int nbk_tree_query_device_ex(const nbk_tree *tree, const float *d_q_aos, uint64_t m, int k,
+                                     int periodic, float box_size, int flags, float *d_out_dist,
+                                     uint32_t *d_out_idx, void *stream);
+
+/* The leaf scan + top-k container in isolation, on ONE flat block of points: the twin of the
+ * reference's C-ABI leaf kernels wenda_insert_closest_l2_avx2 / _periodic_avx2
+ * (kdtree_opt_asm.hpp:12-19,39-63; pinned by tests/test_asm.cpp:97-199 and
+ * tests/test_inserters.cpp:159-220).  x, y, z, idx: n host values each, n % 8 == 0 (the leaf kernels'
+ * own precondition); every query is answered by scanning all n points with the production leaf-scan
+ * code, no tree and no traversal.  Rows as nbk_tree_query_ex2.  device = -1: current. */
+NBK_API int nbk_scan_block(const float *x, const float *y, const float *z, const uint32_t *idx, uint64_t n,
+                           const float *q_aos, uint64_t m, int k, int periodic, float box_size, int flags,
+                           float *out_dist, uint32_t *out_idx, int device);
+
 /* Fused kNN-CDF (the consumer of the (M,k) distance rows PyKDTree::query returns,
- * pybind.cpp:179-188).  For every ks[i] (distinct, 1..64) the distance d to the ks[i]-th neighbour
+ * pybind.cpp:179-188).  For every ks[i] (distinct, >= 1) the distance d to the ks[i]-th neighbour
  * of every query is histogrammed on the device instead of being written out:
  *     counts[i * n_bins + b] += #{queries : edges[b] <= d < edges[b+1]}   (last bin closed)
  * i.e. numpy.histogram(dist[:, ks[i]-1], edges) of the rows nbk_tree_query would return, with one
@@ -183,12 +207,19 @@ NBK_API int nbk_profile_read(int section, double *total_ms, uint64_t *count);
 
 /* ---- device buffers for callers without a GPU array library (results left on the device) ------ */
 NBK_API void *nbk_device_alloc(uint64_t bytes); /* current device; NULL + nbk_last_error() on failure */
+NBK_API void *nbk_device_alloc_on(int device, uint64_t bytes); /* on `device` (-1 = current)          */
+/* Device ordinal a pointer belongs to, -1 for host / unknown memory. */
+NBK_API int nbk_pointer_device(const void *ptr);
 NBK_API void nbk_device_free(void *ptr);
 /* kind: 0 = host -> device, 1 = device -> host; synchronous */
 NBK_API int nbk_device_copy(void *dst, const void *src, uint64_t bytes, int kind);
 NBK_API int nbk_device_zero(void *dst, uint64_t bytes);
 
 /* ---- pinned host staging (optional; speeds up the host-buffer entry points) ---------------- */
+/* How large PAGEABLE host buffers crossed the boundary so far in this process:
+ * out4 = {downloads staged through the pinned ring, downloads copied directly (slow path),
+ *         uploads staged, uploads copied directly}.  Buffers below the staging threshold are not counted. */
+NBK_API int nbk_host_path_stats(uint64_t *out4);
 NBK_API void *nbk_host_alloc(uint64_t bytes);
 NBK_API void nbk_host_free(void *ptr);
 

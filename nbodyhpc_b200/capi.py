@@ -21,14 +21,16 @@ SYMBOLS = [
     "nbk_last_error", "nbk_launch_count", "nbk_device_count",
     "nbk_tree_build", "nbk_tree_build_device", "nbk_tree_build_soa", "nbk_plan_topology", "nbk_tree_free",
     "nbk_tree_get_meta", "nbk_tree_device", "nbk_tree_copy_nodes", "nbk_tree_copy_points",
-    "nbk_tree_query", "nbk_tree_query_device", "nbk_tree_query_ex", "nbk_tree_stats",
+    "nbk_tree_query", "nbk_tree_query_device", "nbk_tree_query_ex", "nbk_tree_query_ex2",
+    "nbk_tree_query_device_ex", "nbk_scan_block", "nbk_tree_stats",
     "nbk_tree_knn_cdf", "nbk_tree_knn_cdf_device",
     "nbk_tree_arena", "nbk_tree_alloc_replica", "nbk_tree_clone_to_device", "nbk_profile_enable", "nbk_profile_read",
-    "nbk_device_alloc", "nbk_device_free", "nbk_device_copy", "nbk_device_zero",
-    "nbk_host_alloc", "nbk_host_free",
+    "nbk_device_alloc", "nbk_device_alloc_on", "nbk_pointer_device", "nbk_device_free", "nbk_device_copy",
+    "nbk_device_zero", "nbk_host_path_stats", "nbk_host_alloc", "nbk_host_free",
 ]
 
 SECTION_QUERY_ORDER, SECTION_KNN_KERNEL = 0, 1
+QUERY_SQUARED = 1  # NBK_QUERY_SQUARED
 
 
 class TreeMeta(C.Structure):
@@ -79,6 +81,9 @@ def lib() -> C.CDLL:
         L.nbk_tree_query.argtypes = [vp, vp, u64, i32, vp, vp]
         L.nbk_tree_query_device.argtypes = [vp, vp, u64, i32, vp, vp, vp]
         L.nbk_tree_query_ex.argtypes = [vp, vp, u64, i32, i32, f32, vp, vp]
+        L.nbk_tree_query_ex2.argtypes = [vp, vp, u64, i32, i32, f32, i32, vp, vp]
+        L.nbk_tree_query_device_ex.argtypes = [vp, vp, u64, i32, i32, f32, i32, vp, vp, vp]
+        L.nbk_scan_block.argtypes = [vp, vp, vp, vp, u64, vp, u64, i32, i32, f32, i32, vp, vp, i32]
         L.nbk_tree_stats.argtypes = [vp, vp, u64, i32, i32, f32, vp]
         L.nbk_tree_knn_cdf.argtypes = [vp, vp, u64, vp, i32, vp, i32, vp]
         L.nbk_tree_knn_cdf_device.argtypes = [vp, vp, u64, vp, i32, vp, i32, vp, vp]
@@ -91,6 +96,10 @@ def lib() -> C.CDLL:
         L.nbk_tree_clone_to_device.argtypes = [vp, i32, ip]
         L.nbk_device_alloc.restype = vp
         L.nbk_device_alloc.argtypes = [u64]
+        L.nbk_device_alloc_on.restype = vp
+        L.nbk_device_alloc_on.argtypes = [i32, u64]
+        L.nbk_pointer_device.argtypes = [vp]
+        L.nbk_host_path_stats.argtypes = [vp]
         L.nbk_device_free.argtypes = [vp]
         L.nbk_device_copy.argtypes = [vp, vp, u64, i32]
         L.nbk_device_zero.argtypes = [vp, u64]
@@ -127,11 +136,38 @@ def plan_topology(n_points: int, leaf_size: int = 64, block_size: int = 8, with_
     return nodes, int(n_nodes.value), int(n_levels.value)
 
 
-def device_alloc(nbytes: int) -> int:
-    p = lib().nbk_device_alloc(nbytes)
+def device_alloc(nbytes: int, device: int = -1) -> int:
+    """cudaMalloc on ``device`` (-1: the calling thread's current device)."""
+    p = lib().nbk_device_alloc_on(device, nbytes)
     if not p:
         raise NbkError(NBK_ERR_NOMEM, lib().nbk_last_error().decode())
     return int(p)
+
+
+def pointer_device(ptr: int) -> int:
+    """Device ordinal owning ``ptr``; -1 for host or unknown memory."""
+    return int(lib().nbk_pointer_device(C.c_void_p(ptr)))
+
+
+def host_path_stats() -> dict:
+    """How large pageable host buffers crossed the boundary so far (staged through pinned memory or not)."""
+    out = np.zeros(4, np.uint64)
+    _check(lib().nbk_host_path_stats(_host_ptr(out)))
+    return dict(zip(("staged_downloads", "direct_downloads", "staged_uploads", "direct_uploads"), map(int, out)))
+
+
+def scan_block(x, y, z, idx, q, k: int, boxsize=None, squared: bool = False, device: int = -1):
+    """The leaf scan + top-k container on ONE flat block of points (no tree): nbk_scan_block."""
+    x, y, z = (np.ascontiguousarray(a, dtype=np.float32) for a in (x, y, z))
+    idx = np.ascontiguousarray(idx, dtype=np.uint32)
+    q = np.ascontiguousarray(q, dtype=np.float32)
+    m = q.shape[0]
+    d = np.empty((m, max(k, 0)), np.float32)
+    i = np.empty((m, max(k, 0)), np.uint32)
+    _check(lib().nbk_scan_block(_host_ptr(x), _host_ptr(y), _host_ptr(z), _host_ptr(idx), x.shape[0], _host_ptr(q), m, k,
+                                int(boxsize is not None), float(boxsize or 0.0), QUERY_SQUARED if squared else 0,
+                                _host_ptr(d), _host_ptr(i), device))
+    return d, i
 
 
 def device_free(ptr: int) -> None:
@@ -270,7 +306,8 @@ class Tree:
         return int(ptr.value), int(nbytes.value)
 
     # ---- query ----------------------------------------------------------------------------
-    def query(self, q: np.ndarray, k: int = 1, periodic: int = -1, boxsize: float = 0.0, out=None):
+    def query(self, q: np.ndarray, k: int = 1, periodic: int = -1, boxsize: float = 0.0, out=None,
+              squared: bool = False):
         q = np.ascontiguousarray(q, dtype=np.float32)
         if q.ndim != 2 or q.shape[1] != 3:
             raise NbkError(NBK_ERR_INVALID, "positions must be a 2D array of shape (N, 3)")
@@ -280,17 +317,20 @@ class Tree:
             i = np.empty((m, max(k, 0)), np.uint32)
         else:
             d, i = out
-        _check(lib().nbk_tree_query_ex(self._h, _host_ptr(q), m, k, periodic, boxsize, _host_ptr(d), _host_ptr(i)))
+        _check(lib().nbk_tree_query_ex2(self._h, _host_ptr(q), m, k, periodic, boxsize, QUERY_SQUARED if squared else 0,
+                                        _host_ptr(d), _host_ptr(i)))
         return d, i
 
     def query_raw(self, q_ptr: int, m: int, k: int, out_d_ptr: int, out_i_ptr: int):
         """Host-pointer entry point (nbk_tree_query) on raw addresses, e.g. pinned torch tensors."""
         _check(lib().nbk_tree_query(self._h, C.c_void_p(q_ptr), m, k, C.c_void_p(out_d_ptr), C.c_void_p(out_i_ptr)))
 
-    def query_device(self, d_q: int, m: int, k: int, d_out_d: int, d_out_i: int, stream: int = 0):
+    def query_device(self, d_q: int, m: int, k: int, d_out_d: int, d_out_i: int, stream: int = 0,
+                     periodic: int = -1, boxsize: float = 0.0, squared: bool = False):
         """Enqueues the query on ``stream`` (a cudaStream_t as int); does not synchronise."""
-        _check(lib().nbk_tree_query_device(self._h, C.c_void_p(d_q), m, k, C.c_void_p(d_out_d), C.c_void_p(d_out_i),
-                                           C.c_void_p(stream)))
+        _check(lib().nbk_tree_query_device_ex(self._h, C.c_void_p(d_q), m, k, periodic, boxsize,
+                                              QUERY_SQUARED if squared else 0, C.c_void_p(d_out_d),
+                                              C.c_void_p(d_out_i), C.c_void_p(stream)))
 
     def knn_cdf(self, q: np.ndarray, ks, edges) -> np.ndarray:
         """counts[i, b] = numpy.histogram(dist[:, ks[i]-1], edges)[0][b] without materialising the rows."""

@@ -8,6 +8,7 @@
 // copy in parallel) while the GPU keeps computing the next slice.
 #pragma once
 
+#include <atomic>
 #include <condition_variable>
 #include <cstring>
 #include <deque>
@@ -19,14 +20,23 @@
 
 namespace nbk {
 
-class PinnedRing { // one per process, allocated on first use, handed to one staged call at a time
+// {staged downloads, direct pageable downloads, staged uploads, direct pageable uploads} (nbk_host_path_stats)
+inline std::atomic<uint64_t> g_host_path[4];
+
+class PinnedRing { // one per device, allocated on first use; a staged call holds it for its duration
   public:
     static constexpr int kSlots = 12; // [0, kUploadSlots): uploads, the rest: downloads
     static constexpr int kUploadSlots = 4;
     static constexpr size_t kSlotBytes = (size_t)32 << 20;
-    static PinnedRing *try_acquire() {
-        static PinnedRing ring;
-        if (!ring.lock_.try_lock()) return nullptr;
+    static constexpr int kMaxDevices = 64;
+    // Blocks while another call on the same device is staging (the transfers of both would share the
+    // same PCIe link anyway); calls on different devices -- KDTree(devices=[...]) runs one host thread
+    // per replica -- have a ring each.  nullptr only if pinned memory cannot be had.
+    static PinnedRing *acquire(int device) {
+        static PinnedRing rings[kMaxDevices];
+        if (device < 0 || device >= kMaxDevices) return nullptr;
+        PinnedRing &ring = rings[device];
+        ring.lock_.lock();
         if (!ring.base_) {
             void *p = nullptr;
             if (cudaHostAlloc(&p, kSlots * kSlotBytes, cudaHostAllocPortable) != cudaSuccess) {

@@ -119,16 +119,26 @@ __device__ __noinline__ float4 d2x4_wrapped(float4 X, float4 Y, float4 Z, float 
     return make_float4(d[0], d[1], d[2], d[3]);
 }
 
+// ---- per-thread binding of a top-k container ---------------------------------------------------------
+struct TopBind {
+    unsigned long long *smem; // the CTA's dynamic shared memory (HeapT<K > 0>)
+    unsigned long long *gmem; // global heap scratch [k][gcolumns] (HeapT<0>: any k)
+    uint32_t gcolumns;
+};
+
 // ---- register-resident top-k ----------------------------------------------------------------------
 // keys sorted ascending; key = (d2 bits << 32) | index, held as two 32-bit halves.  d2 >= +0 so the
 // bit pattern orders like the float.  Empty slots hold (FLT_MAX, 0): a candidate at d2 == FLT_MAX
 // never replaces one (the reference inserts only if d2 < FLT_MAX, kdtree_impl.hpp:210 + strict <).
+// k < K (k = 3, 5, 6, 7): the first K - k slots hold the minimal key (0, 0) and never move, so that
+// worst() is the k-th best and not the K-th (the reference prunes with the k-th, kdtree_impl.hpp:243-262).
 template <int K> struct TopK {
     uint32_t hi[K], lo[K];
-    __device__ __forceinline__ void init() {
+    __device__ __forceinline__ void init(int k) {
+        const int pad = K - k;
 #pragma unroll
         for (int j = 0; j < K; ++j) {
-            hi[j] = kFltMaxBits;
+            hi[j] = j < pad ? 0u : kFltMaxBits;
             lo[j] = 0u;
         }
     }
@@ -136,29 +146,51 @@ template <int K> struct TopK {
     __device__ __forceinline__ bool beats_worst(uint32_t chi, uint32_t clo) const {
         return chi < hi[K - 1] || (chi == hi[K - 1] && clo < lo[K - 1]);
     }
-    __device__ __forceinline__ bool contains(uint32_t chi, uint32_t clo) const {
+    __device__ __forceinline__ bool contains(uint32_t chi, uint32_t clo, int k) const {
+        const int pad = K - k;
         bool hit = false;
 #pragma unroll
-        for (int j = 0; j < K; ++j) hit = hit || (hi[j] == chi && lo[j] == clo);
+        for (int j = 0; j < K; ++j) hit = hit || (j >= pad && hi[j] == chi && lo[j] == clo);
         return hit;
     }
     static constexpr int kSize = K;
     static constexpr bool kShared = false;
-    __device__ __forceinline__ void bind(unsigned long long *) {}
+    static constexpr bool kGlobal = false;
+    __device__ __forceinline__ void bind(TopBind const &) {}
     // f(j, d2 bits) for every rank j (0 = nearest); any order
-    template <typename F> __device__ __forceinline__ void for_each_rank(F &&f) {
+    template <typename F> __device__ __forceinline__ void for_each_rank(int k, F &&f) {
+        const int pad = K - k;
 #pragma unroll
-        for (int j = 0; j < K; ++j) f(j, hi[j]);
+        for (int j = 0; j < K; ++j)
+            if (j >= pad) f(j - pad, hi[j]);
     }
-    __device__ __forceinline__ void write_row(uint32_t qid, int k_out, float *__restrict__ out_d,
+    // raw: squared distances (the d2 the search ranks by) instead of postprocess()'s sqrt
+    __device__ __forceinline__ void write_row(uint32_t qid, int k, bool raw, float *__restrict__ out_d,
                                               uint32_t *__restrict__ out_i) const {
-        float *od = out_d + (uint64_t)qid * k_out;
-        uint32_t *oi = out_i + (uint64_t)qid * k_out;
+        const int pad = K - k;
+        float *od = out_d + (uint64_t)qid * k - pad;
+        uint32_t *oi = out_i + (uint64_t)qid * k - pad;
 #pragma unroll
         for (int j = 0; j < K; ++j) {
-            if (j < k_out) {
-                od[j] = __fsqrt_rn(__uint_as_float(hi[j])); // postprocess, kdtree.cpp:154-156
+            if (j >= pad) {
+                const float d2 = __uint_as_float(hi[j]);
+                od[j] = raw ? d2 : __fsqrt_rn(d2); // postprocess, kdtree.cpp:154-156
                 oi[j] = hi[j] == kFltMaxBits ? 0xFFFFFFFFu : lo[j];
+            }
+        }
+    }
+    // the inverse of write_row(raw = true): resume from a row a previous pass left in the output
+    __device__ __forceinline__ void load_row(uint32_t qid, int k, const float *out_d, const uint32_t *out_i) {
+        const int pad = K - k;
+        const float *od = out_d + (uint64_t)qid * k - pad;
+        const uint32_t *oi = out_i + (uint64_t)qid * k - pad;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            hi[j] = 0u;
+            lo[j] = 0u;
+            if (j >= pad) {
+                hi[j] = __float_as_uint(od[j]);
+                lo[j] = hi[j] == kFltMaxBits ? 0u : oi[j];
             }
         }
     }
@@ -180,26 +212,36 @@ template <int K> struct TopK {
     }
 };
 
-// ---- shared-memory top-k for large k ----------------------------------------------------------------
-// For k > 16 a sorted register list costs O(k) per insertion and most of the register file.  This
-// variant keeps each lane's k best in a binary MAX-heap in shared memory, slot-major
-// (heap[slot * blockDim + thread]: any per-lane slot pattern is bank-conflict free), so that
-// replacing the current worst costs O(log k) like the reference's tournament tree
-// (tournament_tree.hpp:49-91); the root (= current k-th best) is mirrored in registers.  The row is
-// produced by a heap sort in the epilogue.
-template <int K> struct HeapK {
-    static constexpr int kSize = K;
-    static constexpr bool kShared = true;
+// ---- heap top-k for large k ---------------------------------------------------------------------------
+// For k > 8 a sorted register list costs O(k) per insertion and most of the register file.  This
+// variant keeps each lane's k best in a binary MAX-heap of exactly k slots, slot-major so that any
+// per-lane slot pattern is conflict free / coalesced, and replaces the current worst in O(log k) like
+// the reference's tournament tree (tournament_tree.hpp:49-91); the root (= current k-th best) is
+// mirrored in registers.  The row is produced by a heap sort in the epilogue.
+//   KS > 0: heap in shared memory, heap[slot * blockDim + thread], k <= KS
+//   KS = 0: heap in global memory (L2-resident scratch), heap[slot * columns + column]: any k, like the
+//           reference's queue (kdtree.cpp:133-141 accepts every k)
+template <int KS> struct HeapT {
+    static constexpr int kSize = KS;
+    static constexpr bool kShared = KS > 0;
+    static constexpr bool kGlobal = KS == 0;
     unsigned long long *heap; // this thread's column
     uint32_t stride;
-    uint32_t rhi, rlo;         // root
-    __device__ __forceinline__ void bind(unsigned long long *base) {
-        heap = base + threadIdx.x;
-        stride = blockDim.x;
+    int n;            // heap size = k
+    uint32_t rhi, rlo; // root
+    __device__ __forceinline__ void bind(TopBind const &b) {
+        if (KS > 0) {
+            heap = b.smem + threadIdx.x;
+            stride = blockDim.x;
+        } else {
+            heap = b.gmem + ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+            stride = b.gcolumns;
+        }
     }
-    __device__ __forceinline__ unsigned long long &at(int slot) const { return heap[(uint32_t)slot * stride]; }
-    __device__ __forceinline__ void init() {
-        for (int j = 0; j < K; ++j) at(j) = (unsigned long long)kFltMaxBits << 32;
+    __device__ __forceinline__ unsigned long long &at(int slot) const { return heap[(uint64_t)slot * stride]; }
+    __device__ __forceinline__ void init(int k) {
+        n = k;
+        for (int j = 0; j < n; ++j) at(j) = (unsigned long long)kFltMaxBits << 32;
         rhi = kFltMaxBits;
         rlo = 0u;
     }
@@ -207,10 +249,10 @@ template <int K> struct HeapK {
     __device__ __forceinline__ bool beats_worst(uint32_t chi, uint32_t clo) const {
         return chi < rhi || (chi == rhi && clo < rlo);
     }
-    __device__ __forceinline__ bool contains(uint32_t chi, uint32_t clo) const {
+    __device__ __forceinline__ bool contains(uint32_t chi, uint32_t clo, int) const {
         const unsigned long long c = ((unsigned long long)chi << 32) | clo;
         bool hit = false;
-        for (int j = 0; j < K; ++j) hit = hit || at(j) == c;
+        for (int j = 0; j < n; ++j) hit = hit || at(j) == c;
         return hit;
     }
     // sift `c` down from the root of a heap of `size` slots
@@ -232,36 +274,48 @@ template <int K> struct HeapK {
     }
     // precondition: beats_worst(chi, clo): the root (current worst) is replaced
     __device__ __forceinline__ void insert(uint32_t chi, uint32_t clo) {
-        sift_down(((unsigned long long)chi << 32) | clo, K);
+        sift_down(((unsigned long long)chi << 32) | clo, n);
         const unsigned long long root = at(0);
         rhi = (uint32_t)(root >> 32);
         rlo = (uint32_t)root;
     }
     // f(j, d2 bits) for every rank j (0 = nearest), largest first; consumes the heap
-    template <typename F> __device__ __forceinline__ void for_each_rank(F &&f) {
-        for (int size = K; size > 0; --size) {
+    template <typename F> __device__ __forceinline__ void for_each_rank(int, F &&f) {
+        for (int size = n; size > 0; --size) {
             const unsigned long long top = at(0);
             f(size - 1, (uint32_t)(top >> 32));
             if (size > 1) sift_down(at(size - 1), size - 1);
         }
     }
-    __device__ __forceinline__ void write_row(uint32_t qid, int k_out, float *__restrict__ out_d,
+    __device__ __forceinline__ void write_row(uint32_t qid, int k, bool raw, float *__restrict__ out_d,
                                               uint32_t *__restrict__ out_i) {
-        float *od = out_d + (uint64_t)qid * k_out;
-        uint32_t *oi = out_i + (uint64_t)qid * k_out;
+        float *od = out_d + (uint64_t)qid * k;
+        uint32_t *oi = out_i + (uint64_t)qid * k;
         // heap sort: the maximum leaves first and lands at the end of the row
-        for (int size = K; size > 0; --size) {
+        for (int size = n; size > 0; --size) {
             const unsigned long long top = at(0);
-            const int j = size - 1;
-            if (j < k_out) {
-                const uint32_t h = (uint32_t)(top >> 32);
-                od[j] = __fsqrt_rn(__uint_as_float(h)); // postprocess, kdtree.cpp:154-156
-                oi[j] = h == kFltMaxBits ? 0xFFFFFFFFu : (uint32_t)top;
-            }
+            const uint32_t h = (uint32_t)(top >> 32);
+            const float d2 = __uint_as_float(h);
+            od[size - 1] = raw ? d2 : __fsqrt_rn(d2); // postprocess, kdtree.cpp:154-156
+            oi[size - 1] = h == kFltMaxBits ? 0xFFFFFFFFu : (uint32_t)top;
             if (size > 1) sift_down(at(size - 1), size - 1);
         }
     }
+    // the inverse of write_row(raw = true): a row in descending order is a valid max-heap
+    __device__ __forceinline__ void load_row(uint32_t qid, int k, const float *out_d, const uint32_t *out_i) {
+        n = k;
+        const float *od = out_d + (uint64_t)qid * k;
+        const uint32_t *oi = out_i + (uint64_t)qid * k;
+        for (int j = 0; j < n; ++j) {
+            const uint32_t h = __float_as_uint(od[n - 1 - j]);
+            at(j) = ((unsigned long long)h << 32) | (h == kFltMaxBits ? 0u : oi[n - 1 - j]);
+        }
+        const unsigned long long root = at(0);
+        rhi = (uint32_t)(root >> 32);
+        rlo = (uint32_t)root;
+    }
 };
+template <int K> using HeapK = HeapT<K>;
 
 // Scans the tiles [begin, end) of one leaf for this lane's query.  Per 4 points: x, y, z and the
 // indices are four 16-byte loads from one 128-byte tile.  PERIODIC: a wrapped image can only win on
@@ -269,7 +323,7 @@ template <int K> struct HeapK {
 // 3-image formula evaluated.  `dedupe` is set while a shifted image is searched.
 template <typename Top, bool PERIODIC>
 __device__ __forceinline__ void scan_half_tile(const float4 *g, float qx, float qy, float qz, float L,
-                                               float wrap_d2, bool dedupe, Top &top) {
+                                               float wrap_d2, bool dedupe, int k, Top &top) {
     const float4 X = __ldg(g), Y = __ldg(g + 2), Z = __ldg(g + 4);
     float d[4];
     d2x4<false>(X, Y, Z, qx, qy, qz, L, d);
@@ -290,7 +344,7 @@ __device__ __forceinline__ void scan_half_tile(const float4 *g, float qx, float 
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const uint32_t chi = __float_as_uint(d[j]);
-            if (top.beats_worst(chi, idx[j]) && !(dedupe && top.contains(chi, idx[j])))
+            if (top.beats_worst(chi, idx[j]) && !(dedupe && top.contains(chi, idx[j], k)))
                 top.insert(chi, idx[j]);
         }
     }
@@ -298,12 +352,12 @@ __device__ __forceinline__ void scan_half_tile(const float4 *g, float qx, float 
 
 template <typename Top, bool PERIODIC>
 __device__ __forceinline__ void scan_leaf(QueryTree const &t, uint32_t begin, uint32_t end, float qx,
-                                          float qy, float qz, float wrap_d2, bool dedupe, Top &top) {
+                                          float qy, float qz, float wrap_d2, bool dedupe, int k, Top &top) {
     const float4 *tp = t.tiles + (uint64_t)(begin >> 3) * kTileFloat4;
     const float4 *const te = t.tiles + (uint64_t)(end >> 3) * kTileFloat4;
     for (; tp != te; tp += kTileFloat4) {
-        scan_half_tile<Top, PERIODIC>(tp, qx, qy, qz, t.box, wrap_d2, dedupe, top);
-        scan_half_tile<Top, PERIODIC>(tp + 1, qx, qy, qz, t.box, wrap_d2, dedupe, top);
+        scan_half_tile<Top, PERIODIC>(tp, qx, qy, qz, t.box, wrap_d2, dedupe, k, top);
+        scan_half_tile<Top, PERIODIC>(tp + 1, qx, qy, qz, t.box, wrap_d2, dedupe, k, top);
     }
 }
 
@@ -318,10 +372,11 @@ __device__ __forceinline__ void scan_leaf(QueryTree const &t, uint32_t begin, ui
 // (o0, o1, o2) in {0, +L, -L}^3 of the shifted sum, so the tree is searched once per image whose
 // root bound can still beat the current k-th distance.  Almost always that is only the primary
 // image: the fast instantiation (IMAGES = false) searches just that one and, if a shifted image could
-// still matter (the search ball reaches through a face of the box), defers the query to a work list
-// that the general instantiation (IMAGES = true) answers from scratch.  Leaf distances are always
-// the TRUE periodic d2, so a point met again through another image carries the same key and is
-// recognised as a duplicate.
+// still matter (the search ball reaches through a face of the box), hands the query to a work list
+// that the general instantiation (IMAGES = true) finishes: it resumes from the row the fast pass left
+// in the output (raw d2) and searches only the shifted images, or, when no rows are written (kNN-CDF),
+// answers the query from scratch.  Leaf distances are always the TRUE periodic d2, so a point met
+// again through another image carries the same key and is recognised as a duplicate.
 constexpr int kLaneStack = 32; // one pending far child per level; depth <= log2(2^32 / 16)
 constexpr uint32_t kNoNode = 0xFFFFFFFFu;
 
@@ -349,18 +404,31 @@ struct DeferList {
     uint32_t *count;
 };
 
+// What one launch answers.  flags: NBK_QUERY_SQUARED -> rows hold d2 instead of sqrt(d2).
+struct QueryBatch {
+    const float *q_aos;    // (m_total, 3) queries as the caller gave them
+    const uint32_t *order; // this launch's slots -> query ids
+    uint64_t m;            // slots of this launch
+    int k;
+    int flags;
+    float *out_d;          // (m_total, k) rows at the query's own position; null: kNN-CDF only
+    uint32_t *out_i;
+    unsigned long long *gheap; // HeapT<0> scratch
+    uint32_t gcolumns;
+};
+
 // Fused kNN-CDF epilogue: instead of the (M,k) rows, histogram the distance to the
-// k-th neighbour for every k in `kmask` (bit k-1) over `n_bins` bins with edges[0..n_bins]:
-// counts[rank of k in kmask][b] += 1 for edges[b] <= d < edges[b+1], the last bin closed, exactly
-// np.histogram(dist[:, k-1], edges) of the rows the query would have written.
+// j-th neighbour for every rank j with row_of_rank[j] >= 0 over `n_bins` bins with edges[0..n_bins]:
+// counts[row_of_rank[j]][b] += 1 for edges[b] <= d < edges[b+1], the last bin closed, exactly
+// np.histogram(dist[:, j], edges) of the rows the query would have written.
 struct CdfArgs {
     const float *edges;          // null: write rows
-    unsigned long long *counts;  // [popc(kmask)][n_bins]
-    unsigned long long kmask;
+    unsigned long long *counts;  // [rows][n_bins]
+    const int *row_of_rank;      // [k]
     int n_bins;
 };
 
-__device__ __forceinline__ void cdf_accumulate(CdfArgs const &c, int j, uint32_t d2_bits, bool emit) {
+__device__ __forceinline__ void cdf_accumulate(CdfArgs const &c, int row, uint32_t d2_bits, bool emit) {
     // all 32 lanes arrive here together; `emit` says whether this lane has a row
     uint32_t b = 0xFFFFFFFFu;
     if (emit) {
@@ -376,44 +444,23 @@ __device__ __forceinline__ void cdf_accumulate(CdfArgs const &c, int j, uint32_t
         }
     }
     const unsigned peers = __match_any_sync(0xffffffffu, b);
-    if (b != 0xFFFFFFFFu && (int)(threadIdx.x & 31) == __ffs(peers) - 1) {
-        const int row = __popcll(c.kmask & ((1ull << j) - 1ull));
+    if (b != 0xFFFFFFFFu && (int)(threadIdx.x & 31) == __ffs(peers) - 1)
         atomicAdd(&c.counts[(uint64_t)row * c.n_bins + b], (unsigned long long)__popc(peers));
-    }
 }
 
+// One query per lane, all 32 lanes of the warp call this together (`valid` = this lane has a query).
 template <typename Top, bool PERIODIC, bool IMAGES>
-// resident CTAs per SM the register allocation aims for: 9 (56 registers) measured best for K = 8
-// (8: 81.2, 9: 78.8, 10: 78.8 ms per 10^8 queries; 64- and 256-thread CTAs: 79.1 / 81.6); the short
-// lists of K <= 4 fit 48 registers (57.1 -> 54.7 ms at k = 4)
-__global__ void __launch_bounds__(kQueryThreads, (IMAGES || Top::kShared) ? 1
-                                                 : (Top::kSize <= 4 ? NBK_LANE_MIN_BLOCKS + 1 : NBK_LANE_MIN_BLOCKS))
-knn_lane_kernel(QueryTree t, const float *__restrict__ q_aos, const uint32_t *__restrict__ order,
-                uint64_t m, int k_out, float *__restrict__ out_d, uint32_t *__restrict__ out_i,
-                DeferList defer, CdfArgs cdf) {
-    static_assert(PERIODIC || !IMAGES, "image shifts exist only for the periodic metric");
-    uint64_t slot = (uint64_t)blockIdx.x * kQueryThreads + threadIdx.x;
-    bool valid;
-    if (IMAGES) {
-        // second pass: the deferred queries, one per thread of a grid sized for the worst case
-        const uint32_t n = *defer.count;
-        valid = slot < n;
-        if (!__any_sync(0xffffffffu, valid)) return;
-        slot = defer.slots[valid ? slot : 0];
-    } else {
-        valid = slot < m;
-        if (!__any_sync(0xffffffffu, valid)) return;
-    }
-    const uint32_t qid = order[valid ? slot : m - 1];
-    const float qx = q_aos[3 * (uint64_t)qid], qy = q_aos[3 * (uint64_t)qid + 1],
-                qz = q_aos[3 * (uint64_t)qid + 2];
+__device__ __forceinline__ void lane_query(QueryTree const &t, QueryBatch const &a, DeferList const &defer,
+                                           CdfArgs const &cdf, Top &top, uint64_t slot, bool valid) {
+    const uint32_t qid = a.order[valid ? slot : a.m - 1];
+    const float qx = a.q_aos[3 * (uint64_t)qid], qy = a.q_aos[3 * (uint64_t)qid + 1],
+                qz = a.q_aos[3 * (uint64_t)qid + 2];
     const float L = t.box;
     const float wrap_d2 = __fmul_rn(0.5f * L, 0.5f * L);
-
-    extern __shared__ unsigned long long heap_smem[];
-    Top top;
-    top.bind(heap_smem);
-    top.init();
+    const int k = a.k;
+    const bool raw = (a.flags & NBK_QUERY_SQUARED) != 0;
+    // rows mode: the fast pass leaves its (raw) row in the output and the general pass resumes from it
+    const bool carry = a.out_d != nullptr;
 
     float4 stack[kLaneStack]; // (t0, t1, t2, node bits)
     int sp = 0;
@@ -430,6 +477,14 @@ knn_lane_kernel(QueryTree t, const float *__restrict__ q_aos, const uint32_t *__
     uint32_t lbeg = 0, lend = 0;
     uint32_t home = kNoNode; // first point of the leaf that was scanned up front
 
+    if (IMAGES && carry) {
+        if (valid) top.load_row(qid, k, a.out_d, a.out_i);
+        else top.init(k);
+        cur = kNoNode; // the primary image is done: the walk below goes straight to the shifted ones
+    } else {
+        top.init(k);
+    }
+
     if (!IMAGES) {
         // Home leaf first: plain descent to the leaf holding the query (no bounds, nothing pushed);
         // the loop below scans it and only then starts the bounded traversal with a realistic k-th distance,
@@ -437,14 +492,14 @@ knn_lane_kernel(QueryTree t, const float *__restrict__ q_aos, const uint32_t *__
         if (valid) {
             uint32_t nd = 0;
             while (true) {
-                const int4 raw = __ldg(reinterpret_cast<const int4 *>(t.nodes) + nd);
-                if (raw.x < 0) {
-                    lbeg = (uint32_t)raw.z;
-                    lend = (uint32_t)raw.w;
+                const int4 raw_node = __ldg(reinterpret_cast<const int4 *>(t.nodes) + nd);
+                if (raw_node.x < 0) {
+                    lbeg = (uint32_t)raw_node.z;
+                    lend = (uint32_t)raw_node.w;
                     break;
                 }
-                const float qd = raw.x == 0 ? qx : (raw.x == 1 ? qy : qz);
-                nd = __fsub_rn(__int_as_float(raw.y), qd) < 0.0f ? (uint32_t)raw.w : (uint32_t)raw.z;
+                const float qd = raw_node.x == 0 ? qx : (raw_node.x == 1 ? qy : qz);
+                nd = __fsub_rn(__int_as_float(raw_node.y), qd) < 0.0f ? (uint32_t)raw_node.w : (uint32_t)raw_node.z;
             }
             home = lbeg; // the main loop scans [lbeg, lend) first, then starts at the root
         }
@@ -485,23 +540,23 @@ knn_lane_kernel(QueryTree t, const float *__restrict__ q_aos, const uint32_t *__
                 t2 = e.z;
                 cur = __float_as_uint(e.w);
             }
-            const int4 raw = __ldg(reinterpret_cast<const int4 *>(t.nodes) + cur);
-            const int dim = raw.x;
+            const int4 raw_node = __ldg(reinterpret_cast<const int4 *>(t.nodes) + cur);
+            const int dim = raw_node.x;
             if (dim < 0) {
                 cur = kNoNode;
-                if (!IMAGES && (uint32_t)raw.z == home) continue; // already scanned
-                lbeg = (uint32_t)raw.z;
-                lend = (uint32_t)raw.w;
+                if (!IMAGES && (uint32_t)raw_node.z == home) continue; // already scanned
+                lbeg = (uint32_t)raw_node.z;
+                lend = (uint32_t)raw_node.w;
                 break;
             }
-            const float split = __int_as_float(raw.y);
+            const float split = __int_as_float(raw_node.y);
             const float qd = dim == 0 ? qx : (dim == 1 ? qy : qz);
             float w = __fsub_rn(split, qd);
             if (IMAGES) w = __fadd_rn(w, dim == 0 ? o0 : (dim == 1 ? o1 : o2));
             // w > 0: the (shifted) query lies left of the plane -> left child first
             const bool left_first = !(w < 0.0f);
-            const uint32_t near = left_first ? (uint32_t)raw.z : (uint32_t)raw.w;
-            const uint32_t far = left_first ? (uint32_t)raw.w : (uint32_t)raw.z;
+            const uint32_t near = left_first ? (uint32_t)raw_node.z : (uint32_t)raw_node.w;
+            const uint32_t far = left_first ? (uint32_t)raw_node.w : (uint32_t)raw_node.z;
             const float ft = __fmul_rn(w, w);
             const float f0 = dim == 0 ? ft : t0, f1 = dim == 1 ? ft : t1, f2 = dim == 2 ? ft : t2;
             // non-strict: an equal-distance point with a smaller index must still be found
@@ -511,25 +566,85 @@ knn_lane_kernel(QueryTree t, const float *__restrict__ q_aos, const uint32_t *__
         }
         if (!__any_sync(0xffffffffu, lbeg != lend)) break;
         // ---- scan it ------------------------------------------------------------------------------
-        scan_leaf<Top, PERIODIC>(t, lbeg, lend, qx, qy, qz, wrap_d2, IMAGES && img > 0, top);
+        scan_leaf<Top, PERIODIC>(t, lbeg, lend, qx, qy, qz, wrap_d2, IMAGES && img > 0, k, top);
         lbeg = lend = 0;
     }
 
-    bool emit = valid;
+    bool emit = valid, finished = true;
     if (PERIODIC && !IMAGES) {
-        if (valid && min_shifted_root_term(qx, qy, qz, L) <= top.worst()) {
-            defer.slots[atomicAdd(defer.count, 1u)] = (uint32_t)slot;
-            emit = false;
+        // queries whose search ball reaches through a face of the box: one list position per query, the
+        // positions of a warp contiguous (its queries are neighbours, so are their shifted searches)
+        const bool deferred = valid && min_shifted_root_term(qx, qy, qz, L) <= top.worst();
+        const unsigned dmask = __ballot_sync(0xffffffffu, deferred);
+        if (dmask) {
+            const int lane = threadIdx.x & 31;
+            uint32_t base = 0;
+            if (lane == __ffs(dmask) - 1) base = atomicAdd(defer.count, (uint32_t)__popc(dmask));
+            base = __shfl_sync(0xffffffffu, base, __ffs(dmask) - 1);
+            if (deferred) {
+                defer.slots[base + __popc(dmask & ((1u << lane) - 1u))] = (uint32_t)slot;
+                finished = false;
+            }
         }
     }
     if (cdf.edges) {
         // the whole warp walks the ranks together (match_any inside)
-        top.for_each_rank([&](int j, uint32_t d2_bits) {
-            if ((cdf.kmask >> j) & 1ull) cdf_accumulate(cdf, j, d2_bits, emit);
+        emit = emit && finished;
+        top.for_each_rank(k, [&](int j, uint32_t d2_bits) {
+            const int row = __ldg(cdf.row_of_rank + j);
+            if (row >= 0) cdf_accumulate(cdf, row, d2_bits, emit);
         });
         return;
     }
-    if (emit) top.write_row(qid, k_out, out_d, out_i);
+    if (emit) top.write_row(qid, k, raw || !finished, a.out_d, a.out_i);
+}
+
+template <typename Top, bool PERIODIC, bool IMAGES>
+// resident CTAs per SM the register allocation aims for: 9 (56 registers) measured best for K = 8
+// (8: 81.2, 9: 78.8, 10: 78.8 ms per 10^8 queries; 64- and 256-thread CTAs: 79.1 / 81.6); the short
+// lists of K <= 4 fit 48 registers (57.1 -> 54.7 ms at k = 4)
+__global__ void __launch_bounds__(kQueryThreads, (IMAGES || Top::kShared || Top::kGlobal) ? 1
+                                                 : (Top::kSize <= 4 ? NBK_LANE_MIN_BLOCKS + 1 : NBK_LANE_MIN_BLOCKS))
+knn_lane_kernel(QueryTree t, QueryBatch a, DeferList defer, CdfArgs cdf) {
+    static_assert(PERIODIC || !IMAGES, "image shifts exist only for the periodic metric");
+    extern __shared__ unsigned long long heap_smem[];
+    Top top;
+    top.bind(TopBind{heap_smem, a.gheap, a.gcolumns});
+    if (IMAGES) {
+        // second pass: a persistent grid walks the work list, 32 consecutive entries per warp and turn
+        const uint32_t n = *defer.count;
+        const uint32_t turn = gridDim.x * kQueryThreads;
+        for (uint32_t base = blockIdx.x * kQueryThreads + (threadIdx.x & ~31u); base < n; base += turn) {
+            const uint32_t pos = base + (threadIdx.x & 31u);
+            const bool valid = pos < n;
+            lane_query<Top, PERIODIC, IMAGES>(t, a, defer, cdf, top, defer.slots[valid ? pos : base], valid);
+        }
+    } else {
+        const uint64_t slot = (uint64_t)blockIdx.x * kQueryThreads + threadIdx.x;
+        const bool valid = slot < a.m;
+        if (!__any_sync(0xffffffffu, valid)) return;
+        lane_query<Top, PERIODIC, IMAGES>(t, a, defer, cdf, top, slot, valid);
+    }
+}
+
+// ---- flat block scan: the leaf scan + top-k in isolation (test hook) --------------------------------
+// The twin of the reference's leaf kernel called on one flat block (wenda_insert_closest_l2[_periodic]_avx2,
+// kdtree_opt_asm.hpp:12-19; pinned by tests/test_asm.cpp:97-199 and tests/test_inserters.cpp:159-220):
+// every thread scans ALL n points (tiles [0, n)) for its query with the production scan_leaf + container
+// and writes the row.  No tree, no traversal.
+template <typename Top, bool PERIODIC>
+__global__ void __launch_bounds__(kQueryThreads)
+scan_block_kernel(QueryTree t, uint32_t n, QueryBatch a) {
+    extern __shared__ unsigned long long heap_smem[];
+    const uint64_t slot = (uint64_t)blockIdx.x * kQueryThreads + threadIdx.x;
+    if (slot >= a.m) return;
+    Top top;
+    top.bind(TopBind{heap_smem, a.gheap, a.gcolumns});
+    top.init(a.k);
+    const float qx = a.q_aos[3 * slot], qy = a.q_aos[3 * slot + 1], qz = a.q_aos[3 * slot + 2];
+    const float wrap_d2 = __fmul_rn(0.5f * t.box, 0.5f * t.box);
+    scan_leaf<Top, PERIODIC>(t, 0u, n, qx, qy, qz, wrap_d2, false, a.k, top);
+    top.write_row((uint32_t)slot, a.k, (a.flags & NBK_QUERY_SQUARED) != 0, a.out_d, a.out_i);
 }
 
 // ---- the packet kernel -----------------------------------------------------------------------------
@@ -565,7 +680,7 @@ __device__ __forceinline__ float axis_lb_periodic(float a, float b, float L) {
 template <int K, bool PERIODIC>
 __global__ void __launch_bounds__(kQueryThreads)
 knn_packet_kernel(QueryTree t, const float *__restrict__ q_aos, const uint32_t *__restrict__ order,
-                  uint64_t m, int k_out, float *__restrict__ out_d, uint32_t *__restrict__ out_i) {
+                  uint64_t m, int k_out, bool raw, float *__restrict__ out_d, uint32_t *__restrict__ out_i) {
     __shared__ StackEntry stack[kQueryWarps][kMaxStack];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t slot = (uint64_t)blockIdx.x * kQueryThreads + threadIdx.x;
@@ -577,7 +692,7 @@ knn_packet_kernel(QueryTree t, const float *__restrict__ q_aos, const uint32_t *
     const float wrap_d2 = __fmul_rn(0.5f * t.box, 0.5f * t.box);
 
     TopK<K> top;
-    top.init();
+    top.init(k_out);
 
     StackEntry *st = stack[warp];
     if (lane == 0) st[0] = StackEntry{t.lo[0], t.lo[1], t.lo[2], 0u, t.hi[0], t.hi[1], t.hi[2], 0u};
@@ -604,7 +719,7 @@ knn_packet_kernel(QueryTree t, const float *__restrict__ q_aos, const uint32_t *
         const nbk_node nd = *reinterpret_cast<const nbk_node *>(
             &reinterpret_cast<const int4 *>(t.nodes)[e.node]);
         if (nd.dim < 0) {
-            scan_leaf<TopK<K>, PERIODIC>(t, nd.left, nd.right, qx, qy, qz, wrap_d2, false, top);
+            scan_leaf<TopK<K>, PERIODIC>(t, nd.left, nd.right, qx, qy, qz, wrap_d2, false, k_out, top);
             continue;
         }
         const float qd = nd.dim == 0 ? qx : (nd.dim == 1 ? qy : qz);
@@ -623,7 +738,7 @@ knn_packet_kernel(QueryTree t, const float *__restrict__ q_aos, const uint32_t *
         __syncwarp();
         sp += 2;
     }
-    if (valid) top.write_row(qid, k_out, out_d, out_i);
+    if (valid) top.write_row(qid, k_out, raw, out_d, out_i);
 }
 
 // ---- KDTreeQueryStatistics: the reference's own traversal, one thread per query -----------------
@@ -657,13 +772,14 @@ constexpr int kStatsMaxK = 64;
 
 template <bool PERIODIC>
 __global__ void __launch_bounds__(128)
-stats_kernel(QueryTree t, const float *__restrict__ q_aos, uint64_t m, int k,
+stats_kernel(QueryTree t, const float *__restrict__ q_aos, uint64_t m, int k, float *__restrict__ gbest,
              unsigned long long *__restrict__ out3) {
     uint64_t i = (uint64_t)blockIdx.x * 128 + threadIdx.x;
     unsigned long long nv = 0, np = 0, pv = 0;
     if (i < m) {
         const float q[3] = {q_aos[3 * i], q_aos[3 * i + 1], q_aos[3 * i + 2]};
-        float best[kStatsMaxK]; // unsorted, track the maximum like a replace-top queue
+        float local_best[kStatsMaxK]; // unsorted, track the maximum like a replace-top queue
+        float *best = k <= kStatsMaxK ? local_best : gbest + i * (uint64_t)k; // k > 64: global scratch row
         for (int j = 0; j < k; ++j) best[j] = FLT_MAX;
         int top = 0;
         // explicit stack of (node, bounds, stage): stage 0 = entering, 1 = closer child done

@@ -50,6 +50,46 @@ struct nbk_tree {
     int device = 0;
     char *arena = nullptr;
     nbk::TreeArena view{};
+    // streams that have read this tree since it was built, with an event marking their last use: the
+    // arena is released behind them instead of behind a device-wide synchronisation
+    mutable std::mutex use_mutex;
+    mutable std::vector<std::pair<cudaStream_t, cudaEvent_t>> uses;
+
+    nbk_tree() = default;
+    nbk_tree(nbk_tree const &) = delete;
+    ~nbk_tree() {
+        int prev = -1;
+        cudaGetDevice(&prev);
+        cudaSetDevice(device);
+        for (auto &u : uses) {
+            cudaStreamWaitEvent(nullptr, u.second, 0);
+            cudaEventDestroy(u.second);
+        }
+        if (arena) cudaFreeAsync(arena, nullptr);
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    // called after work reading the tree has been enqueued on `stream`
+    void mark_use(cudaStream_t stream) const {
+        if (stream == nullptr || stream == cudaStreamLegacy) return; // the release itself is ordered on this stream
+        std::lock_guard<std::mutex> lock(use_mutex);
+        for (auto &u : uses)
+            if (u.first == stream) {
+                cudaEventRecord(u.second, stream);
+                return;
+            }
+        if (uses.size() >= 64) {
+            // a caller cycling through short-lived streams: settle the old ones instead of growing
+            for (auto &u : uses) {
+                cudaEventSynchronize(u.second);
+                cudaEventDestroy(u.second);
+            }
+            uses.clear();
+        }
+        cudaEvent_t ev = nullptr;
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return;
+        cudaEventRecord(ev, stream);
+        uses.emplace_back(stream, ev);
+    }
 
     void bind() {
         nbk::ArenaLayout l = nbk::arena_layout(meta.n_padded, meta.n_nodes);
@@ -126,15 +166,16 @@ void check_build_args(uint64_t n_padded, int block_size, bool soa) {
         throw Error(NBK_ERR_INVALID, "block_size must divide the number of points.");
 }
 
-std::unique_ptr<nbk_tree> alloc_tree(nbk_tree_meta const &meta, int device) {
+// The arena comes from the stream-ordered pool, allocated on the stream that fills it (a tree freed
+// and rebuilt reuses the same memory); ~nbk_tree releases it behind every stream that used it.
+std::unique_ptr<nbk_tree> alloc_tree(nbk_tree_meta const &meta, cudaStream_t stream) {
     auto t = std::make_unique<nbk_tree>();
     t->meta = meta;
     NBK_CUDA(cudaGetDevice(&t->device));
-    (void)device;
     ArenaLayout l = arena_layout(meta.n_padded, meta.n_nodes);
     t->meta.arena_bytes = l.total;
-    // from the stream-ordered pool (legacy stream): a tree freed and rebuilt reuses the same memory
-    NBK_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&t->arena), l.total, nullptr));
+    NBK_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&t->arena), l.total, stream));
+    t->mark_use(stream);
     t->bind();
     return t;
 }
@@ -161,7 +202,8 @@ std::unique_ptr<nbk_tree> finish_build(uint64_t n, uint64_t n_padded, int leaf_s
     meta.periodic = periodic ? 1 : 0;
     meta.box_size = periodic ? box_size : 0.0f;
     meta.n_levels = top.n_levels;
-    auto tree = alloc_tree(meta, device);
+    (void)device;
+    auto tree = alloc_tree(meta, stream);
     uint64_t scratch_bytes = n_padded * 16; // the caller's columns
     if (sort_build) {
         TopologyPlan plan = plan_topology(n_padded, leaf_size, block_size);
@@ -287,19 +329,14 @@ inline bool use_packet_kernel() {
     return packet;
 }
 
-// k <= 8: sorted register list; above: shared-memory heap (NBK_HEAP_FROM overrides the threshold)
-inline int heap_from_k() {
-    static const int v = [] {
-        const char *e = std::getenv("NBK_HEAP_FROM");
-        return e ? std::atoi(e) : 9;
-    }();
-    return v;
-}
+constexpr int kMaxSharedK = 64; // above: heaps in global memory
+
+// second (shifted images) pass: a persistent grid over the device-side work list
+constexpr unsigned kImagesGridMax = 148 * 8;
 
 template <typename Top, bool P>
-void launch_lane(QueryTree const &qt, const float *d_q, const uint32_t *order, uint64_t m, int k,
-                 float *d_out_d, uint32_t *d_out_i, DeferList defer, CdfArgs cdf, cudaStream_t stream) {
-    unsigned grid = (unsigned)div_up(m, kQueryThreads);
+void launch_lane(QueryTree const &qt, QueryBatch const &qb, DeferList defer, CdfArgs cdf, cudaStream_t stream) {
+    unsigned grid = (unsigned)div_up(qb.m, kQueryThreads);
     size_t smem = Top::kShared ? (size_t)Top::kSize * kQueryThreads * sizeof(unsigned long long) : 0;
     auto fast = knn_lane_kernel<Top, P, false>;
     auto general = knn_lane_kernel<Top, P, P>;
@@ -307,54 +344,86 @@ void launch_lane(QueryTree const &qt, const float *d_q, const uint32_t *order, u
         NBK_CUDA(cudaFuncSetAttribute(fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         NBK_CUDA(cudaFuncSetAttribute(general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    fast<<<grid, kQueryThreads, smem, stream>>>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, cdf);
+    fast<<<grid, kQueryThreads, smem, stream>>>(qt, qb, defer, cdf);
     NBK_LAUNCHED();
     if (P) {
-        // queries whose search ball reaches through a face of the box (usually ~1 %): answered from
-        // scratch over all relevant image shifts; the kernel reads the count on the device
-        general<<<grid, kQueryThreads, smem, stream>>>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, cdf);
+        // queries whose search ball reaches through a face of the box (usually ~1 %): the kernel reads
+        // their number on the device and walks the list with a grid that fits the machine once
+        general<<<std::min(grid, kImagesGridMax), kQueryThreads, smem, stream>>>(qt, qb, defer, cdf);
         NBK_LAUNCHED();
     }
 }
 
 template <int K, bool P>
-void launch_knn(QueryTree const &qt, const float *d_q, const uint32_t *order, uint64_t m, int k,
-                float *d_out_d, uint32_t *d_out_i, DeferList defer, CdfArgs cdf, cudaStream_t stream) {
+void launch_knn(QueryTree const &qt, QueryBatch const &qb, DeferList defer, CdfArgs cdf, cudaStream_t stream) {
     if (use_packet_kernel()) {
         if (cdf.edges) throw Error(NBK_ERR_INVALID, "the kNN-CDF epilogue needs the default (lane) kernel");
-        unsigned grid = (unsigned)div_up(m, kQueryThreads);
-        knn_packet_kernel<K, P><<<grid, kQueryThreads, 0, stream>>>(qt, d_q, order, m, k, d_out_d, d_out_i);
-        NBK_LAUNCHED();
-        return;
-    }
-    if constexpr (K >= 16) {
-        if (k >= heap_from_k()) {
-            launch_lane<HeapK<K>, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, cdf, stream);
+        if constexpr (K > 0 && K <= 8) {
+            unsigned grid = (unsigned)div_up(qb.m, kQueryThreads);
+            knn_packet_kernel<K, P><<<grid, kQueryThreads, 0, stream>>>(qt, qb.q_aos, qb.order, qb.m, qb.k,
+                                                                        (qb.flags & NBK_QUERY_SQUARED) != 0,
+                                                                        qb.out_d, qb.out_i);
+            NBK_LAUNCHED();
             return;
         }
     }
-    launch_lane<TopK<K>, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, cdf, stream);
+    if constexpr (K == 0) {
+        launch_lane<HeapT<0>, P>(qt, qb, defer, cdf, stream);
+    } else if constexpr (K >= 16) {
+        launch_lane<HeapT<K>, P>(qt, qb, defer, cdf, stream);
+    } else {
+        launch_lane<TopK<K>, P>(qt, qb, defer, cdf, stream);
+    }
 }
 
 template <bool P>
-void dispatch_knn(QueryTree const &qt, const float *d_q, const uint32_t *order, uint64_t m, int k,
-                  float *d_out_d, uint32_t *d_out_i, DeferList defer, CdfArgs cdf, cudaStream_t stream) {
-    if (k <= 1) launch_knn<1, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, cdf, stream);
-    else if (k <= 2) launch_knn<2, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, cdf, stream);
-    else if (k <= 4) launch_knn<4, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, cdf, stream);
-    else if (k <= 8) launch_knn<8, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, cdf, stream);
-    else if (k <= 16) launch_knn<16, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, cdf, stream);
-    else if (k <= 32) launch_knn<32, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, cdf, stream);
-    else launch_knn<64, P>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, cdf, stream);
+void dispatch_knn(QueryTree const &qt, QueryBatch const &qb, DeferList defer, CdfArgs cdf, cudaStream_t stream) {
+    const int k = qb.k;
+    if (k <= 1) launch_knn<1, P>(qt, qb, defer, cdf, stream);
+    else if (k <= 2) launch_knn<2, P>(qt, qb, defer, cdf, stream);
+    else if (k <= 4) launch_knn<4, P>(qt, qb, defer, cdf, stream);
+    else if (k <= 8) launch_knn<8, P>(qt, qb, defer, cdf, stream);
+    else if (k <= 16) launch_knn<16, P>(qt, qb, defer, cdf, stream);
+    else if (k <= 32) launch_knn<32, P>(qt, qb, defer, cdf, stream);
+    else if (k <= 64) launch_knn<64, P>(qt, qb, defer, cdf, stream);
+    else launch_knn<0, P>(qt, qb, defer, cdf, stream);
 }
 
-constexpr int kMaxK = 64;
+template <typename Top, bool P>
+void launch_scan_block(QueryTree const &qt, uint32_t n, QueryBatch const &qb, cudaStream_t stream) {
+    size_t smem = Top::kShared ? (size_t)Top::kSize * kQueryThreads * sizeof(unsigned long long) : 0;
+    auto kern = scan_block_kernel<Top, P>;
+    if (smem > 48 * 1024) NBK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)div_up(qb.m, kQueryThreads), kQueryThreads, smem, stream>>>(qt, n, qb);
+    NBK_LAUNCHED();
+}
+
+// the same k -> container choice as dispatch_knn
+template <bool P> void dispatch_scan_block(QueryTree const &qt, uint32_t n, QueryBatch const &qb, cudaStream_t stream) {
+    const int k = qb.k;
+    if (k <= 1) launch_scan_block<TopK<1>, P>(qt, n, qb, stream);
+    else if (k <= 2) launch_scan_block<TopK<2>, P>(qt, n, qb, stream);
+    else if (k <= 4) launch_scan_block<TopK<4>, P>(qt, n, qb, stream);
+    else if (k <= 8) launch_scan_block<TopK<8>, P>(qt, n, qb, stream);
+    else if (k <= 16) launch_scan_block<HeapT<16>, P>(qt, n, qb, stream);
+    else if (k <= 32) launch_scan_block<HeapT<32>, P>(qt, n, qb, stream);
+    else if (k <= 64) launch_scan_block<HeapT<64>, P>(qt, n, qb, stream);
+    else launch_scan_block<HeapT<0>, P>(qt, n, qb, stream);
+}
+
+// k > 64: heaps of exactly k slots in a global scratch of `columns` heaps, answered batch by batch.
+// The scratch is sized to stay L2-resident-ish (<= 256 MB) while a batch still fills the machine.
+inline uint64_t global_heap_columns(int k) {
+    const uint64_t by_bytes = (256ull << 20) / ((uint64_t)k * 8);
+    const uint64_t cols = std::max<uint64_t>(148ull * 4 * kQueryThreads, std::min<uint64_t>(by_bytes, 1ull << 20));
+    return align_up(cols, kQueryThreads);
+}
 
 void query_device(nbk_tree const &tree, const float *d_q, uint64_t m, int k, float *d_out_d,
                   uint32_t *d_out_i, cudaStream_t stream, int periodic = -1, float box_size = 0.0f,
-                  CdfArgs cdf = CdfArgs{nullptr, nullptr, 0ull, 0}) {
+                  CdfArgs cdf = CdfArgs{nullptr, nullptr, nullptr, 0}, int flags = 0) {
     if (k <= 0) throw Error(NBK_ERR_INVALID, "k must be positive integer"); // pybind.cpp:92-94
-    if (k > kMaxK) throw Error(NBK_ERR_INVALID, "k > 64 is not supported by this build");
+    if (flags & ~NBK_QUERY_SQUARED) throw Error(NBK_ERR_INVALID, "unknown query flag");
     if (m == 0) return;
     if (m > 0xFFFFFFFFull) throw Error(NBK_ERR_INVALID, "more than 2^32-1 queries per call");
     Scratch scratch(stream);
@@ -392,19 +461,29 @@ void query_device(nbk_tree const &tree, const float *d_q, uint64_t m, int k, flo
         // the sort's input buffers are free again: reuse one as the deferred-query list
         defer.slots = where ? keys_a : keys_b;
         defer.count = scratch.get<uint32_t>(1);
-        NBK_CUDA(cudaMemsetAsync(defer.count, 0, 4, stream));
     }
-    if (qt.periodic) dispatch_knn<true>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, cdf, stream);
-    else dispatch_knn<false>(qt, d_q, order, m, k, d_out_d, d_out_i, defer, cdf, stream);
+    QueryBatch qb{d_q, order, m, k, flags, d_out_d, d_out_i, nullptr, 0u};
+    uint64_t batch = m;
+    if (k > kMaxSharedK) {
+        const uint64_t cols = global_heap_columns(k);
+        qb.gheap = scratch.get<unsigned long long>(cols * (uint64_t)k);
+        qb.gcolumns = (uint32_t)cols;
+        batch = cols;
+    }
+    for (uint64_t begin = 0; begin < m; begin += batch) {
+        qb.order = order + begin;
+        qb.m = std::min(batch, m - begin);
+        if (defer.count) NBK_CUDA(cudaMemsetAsync(defer.count, 0, 4, stream));
+        if (qt.periodic) dispatch_knn<true>(qt, qb, defer, cdf, stream);
+        else dispatch_knn<false>(qt, qb, defer, cdf, stream);
+    }
     t_knn.finish();
 }
 
-// kNN-CDF: ks may come in any order; rows of `d_counts` follow that order.  Internally rows are in
-// ascending-k order (the kernel indexes them by popcount of the mask); `perm_rows` maps them back.
+// kNN-CDF: ks may come in any order; row i of `d_counts` belongs to ks[i].
 struct CdfPlan {
-    unsigned long long kmask = 0;
     int kmax = 0;
-    std::vector<int> row_of; // row_of[i] = internal row of ks[i]
+    std::vector<int> row_of_rank; // [kmax]: row of the histogram of rank j (= k - 1), or -1
 };
 
 CdfPlan plan_cdf(const int *ks, int n_ks, int n_bins) {
@@ -413,39 +492,27 @@ CdfPlan plan_cdf(const int *ks, int n_ks, int n_bins) {
     CdfPlan p;
     for (int i = 0; i < n_ks; ++i) {
         if (ks[i] <= 0) throw Error(NBK_ERR_INVALID, "k must be positive integer");
-        if (ks[i] > kMaxK) throw Error(NBK_ERR_INVALID, "k > 64 is not supported by this build");
-        if (p.kmask & (1ull << (ks[i] - 1))) throw Error(NBK_ERR_INVALID, "ks must be distinct");
-        p.kmask |= 1ull << (ks[i] - 1);
         p.kmax = std::max(p.kmax, ks[i]);
     }
-    p.row_of.resize(n_ks);
-    for (int i = 0; i < n_ks; ++i) p.row_of[i] = __builtin_popcountll(p.kmask & ((1ull << (ks[i] - 1)) - 1ull));
+    p.row_of_rank.assign(p.kmax, -1);
+    for (int i = 0; i < n_ks; ++i) {
+        if (p.row_of_rank[ks[i] - 1] >= 0) throw Error(NBK_ERR_INVALID, "ks must be distinct");
+        p.row_of_rank[ks[i] - 1] = i;
+    }
     return p;
-}
-
-__global__ void add_rows_kernel(const unsigned long long *__restrict__ src, unsigned long long *__restrict__ dst,
-                                const int *__restrict__ row_of, int n_ks, int n_bins) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_ks * n_bins) return;
-    const int r = i / n_bins, b = i - r * n_bins;
-    dst[i] += src[(uint64_t)row_of[r] * n_bins + b];
 }
 
 // d_counts[i][b] += histogram of the ks[i]-th neighbour distance; everything on `stream`
 void knn_cdf_device(nbk_tree const &tree, const float *d_q, uint64_t m, CdfPlan const &plan, int n_ks,
                     const float *d_edges, int n_bins, unsigned long long *d_counts, cudaStream_t stream) {
+    (void)n_ks;
     if (m == 0) return;
     Scratch scratch(stream);
-    unsigned long long *tmp = scratch.get<unsigned long long>((uint64_t)n_ks * n_bins);
-    int *d_row = scratch.get<int>(n_ks);
-    NBK_CUDA(cudaMemsetAsync(tmp, 0, (uint64_t)n_ks * n_bins * 8, stream));
-    NBK_CUDA(cudaMemcpyAsync(d_row, plan.row_of.data(), n_ks * sizeof(int), cudaMemcpyHostToDevice, stream));
-    CdfArgs cdf{d_edges, tmp, plan.kmask, n_bins};
+    int *d_row = scratch.get<int>(plan.kmax);
+    NBK_CUDA(cudaMemcpyAsync(d_row, plan.row_of_rank.data(), plan.kmax * sizeof(int), cudaMemcpyHostToDevice, stream));
+    CdfArgs cdf{d_edges, d_counts, d_row, n_bins};
     query_device(tree, d_q, m, plan.kmax, nullptr, nullptr, stream, -1, 0.0f, cdf);
-    const int total = n_ks * n_bins;
-    add_rows_kernel<<<(unsigned)div_up(total, 256), 256, 0, stream>>>(tmp, d_counts, d_row, n_ks, n_bins);
-    NBK_LAUNCHED();
-    NBK_CUDA(cudaStreamSynchronize(stream)); // plan.row_of must outlive the copy
+    NBK_CUDA(cudaStreamSynchronize(stream)); // plan.row_of_rank must outlive the copy
 }
 
 } // namespace nbk
@@ -488,14 +555,16 @@ nbk_tree *nbk_tree_build(const float *xyz_aos, uint64_t n, int leaf_size, int bl
             float *d_aos = staging.get<float>(std::max<uint64_t>(n, 1) * 3);
             const double t_alloc = since();
             {
-                PinnedRing *ring = (n * 12ull >= (32u << 20) && is_pageable_host(xyz_aos)) ? PinnedRing::try_acquire() : nullptr;
+                const bool big_pageable = n * 12ull >= (32u << 20) && is_pageable_host(xyz_aos);
+                int dev = 0;
+                NBK_CUDA(cudaGetDevice(&dev));
+                PinnedRing *ring = big_pageable ? PinnedRing::acquire(dev) : nullptr;
+                if (big_pageable) g_host_path[ring ? 2 : 3].fetch_add(1);
                 if (ring) {
                     struct Release {
                         PinnedRing *r;
                         ~Release() { r->release(); }
                     } release{ring};
-                    int dev = 0;
-                    NBK_CUDA(cudaGetDevice(&dev));
                     static const int threads = (int)std::min(8u, std::max(2u, std::thread::hardware_concurrency() / 2));
                     StagedUpload up(ring, dev, threads);
                     up.upload(d_aos, xyz_aos, n * 12, stream);
@@ -597,13 +666,8 @@ int nbk_plan_topology(uint64_t n_points, int leaf_size, int block_size, nbk_node
 }
 
 void nbk_tree_free(nbk_tree *tree) {
-    if (!tree) return;
-    int prev = -1;
-    cudaGetDevice(&prev);
-    cudaSetDevice(tree->device);
-    cudaDeviceSynchronize(); // queries may still be running on caller streams (cudaFree used to imply this)
-    cudaFreeAsync(tree->arena, nullptr);
-    if (prev >= 0) cudaSetDevice(prev);
+    // ~nbk_tree orders the release of the arena behind the last use on every stream that queried the
+    // tree (no device-wide synchronisation: other trees' work keeps running)
     delete tree;
 }
 
@@ -648,10 +712,17 @@ int nbk_tree_copy_points(const nbk_tree *tree, float *x, float *y, float *z, uin
 
 int nbk_tree_query_device(const nbk_tree *tree, const float *d_q_aos, uint64_t m, int k,
                           float *d_out_dist, uint32_t *d_out_idx, void *stream) {
+    return nbk_tree_query_device_ex(tree, d_q_aos, m, k, -1, 0.0f, 0, d_out_dist, d_out_idx, stream);
+}
+
+int nbk_tree_query_device_ex(const nbk_tree *tree, const float *d_q_aos, uint64_t m, int k, int periodic,
+                             float box_size, int flags, float *d_out_dist, uint32_t *d_out_idx, void *stream) {
     return guarded([&] {
         if (!tree) throw Error(NBK_ERR_INVALID, "null argument");
         DeviceGuard guard(tree->device);
-        query_device(*tree, d_q_aos, m, k, d_out_dist, d_out_idx, static_cast<cudaStream_t>(stream));
+        query_device(*tree, d_q_aos, m, k, d_out_dist, d_out_idx, static_cast<cudaStream_t>(stream), periodic,
+                     box_size, CdfArgs{nullptr, nullptr, nullptr, 0}, flags);
+        tree->mark_use(static_cast<cudaStream_t>(stream)); // the call does not synchronise
     });
 }
 
@@ -662,10 +733,15 @@ int nbk_tree_query(const nbk_tree *tree, const float *q_aos, uint64_t m, int k, 
 
 int nbk_tree_query_ex(const nbk_tree *tree, const float *q_aos, uint64_t m, int k, int periodic,
                       float box_size, float *out_dist, uint32_t *out_idx) {
+    return nbk_tree_query_ex2(tree, q_aos, m, k, periodic, box_size, 0, out_dist, out_idx);
+}
+
+int nbk_tree_query_ex2(const nbk_tree *tree, const float *q_aos, uint64_t m, int k, int periodic,
+                       float box_size, int flags, float *out_dist, uint32_t *out_idx) {
     return guarded([&] {
         if (!tree) throw Error(NBK_ERR_INVALID, "null argument");
         if (k <= 0) throw Error(NBK_ERR_INVALID, "k must be positive integer");
-        if (k > kMaxK) throw Error(NBK_ERR_INVALID, "k > 64 is not supported by this build");
+        if (flags & ~NBK_QUERY_SQUARED) throw Error(NBK_ERR_INVALID, "unknown query flag");
         if (m == 0) return;
         DeviceGuard guard(tree->device);
         // Up to three slices in flight, one stream each: slice c+2 uploads while slice c+1 computes
@@ -709,21 +785,29 @@ int nbk_tree_query_ex(const nbk_tree *tree, const float *q_aos, uint64_t m, int 
         std::unique_ptr<StagedDownload> staged;
         PinnedRing *staged_ring = nullptr;
         if (m * (uint64_t)k * 8 >= (64u << 20) && is_pageable_host(out_dist) && is_pageable_host(out_idx)) {
-            if ((staged_ring = PinnedRing::try_acquire()))
-                staged = std::make_unique<StagedDownload>(staged_ring, tree->device, host_threads);
+            if ((staged_ring = PinnedRing::acquire(tree->device))) {
+                try {
+                    staged = std::make_unique<StagedDownload>(staged_ring, tree->device, host_threads);
+                } catch (...) {
+                    staged_ring->release();
+                    throw;
+                }
+            }
+            g_host_path[staged ? 0 : 1].fetch_add(1);
         }
         std::unique_ptr<StagedUpload> uploader;
         PinnedRing *upload_ring = nullptr;
         if (m * 12ull >= (32u << 20) && is_pageable_host(q_aos)) {
             // shares the ring of the staged download if there is one, otherwise takes it for itself
             if (staged) upload_ring = staged_ring;
-            else upload_ring = PinnedRing::try_acquire();
-            if (upload_ring) uploader = std::make_unique<StagedUpload>(upload_ring, tree->device, std::max(2, host_threads / 2));
+            else upload_ring = PinnedRing::acquire(tree->device);
+            g_host_path[upload_ring ? 2 : 3].fetch_add(1);
         }
         struct RingRelease {
             PinnedRing *ring;
             ~RingRelease() { if (ring) ring->release(); }
         } upload_ring_release{staged ? nullptr : upload_ring};
+        if (upload_ring) uploader = std::make_unique<StagedUpload>(upload_ring, tree->device, std::max(2, host_threads / 2));
         auto download = [&](int s, uint64_t begin, uint64_t cnt) {
             const uint64_t bytes = cnt * (uint64_t)k * 4;
             if (staged) {
@@ -752,7 +836,8 @@ int nbk_tree_query_ex(const nbk_tree *tree, const float *q_aos, uint64_t m, int 
                 cudaStream_t st = streams[s];
                 if (uploader) uploader->upload(d_q[s], q_aos + begin * 3, cnt * 12, st);
                 else NBK_CUDA(cudaMemcpyAsync(d_q[s], q_aos + begin * 3, cnt * 12, cudaMemcpyHostToDevice, st));
-                query_device(*tree, d_q[s], cnt, k, d_d[s], d_i[s], st, periodic, box_size);
+                query_device(*tree, d_q[s], cnt, k, d_d[s], d_i[s], st, periodic, box_size,
+                             CdfArgs{nullptr, nullptr, nullptr, 0}, flags);
                 if (pend_s >= 0) download(pend_s, pend_begin, pend_cnt);
                 pend_s = s;
                 pend_begin = begin;
@@ -772,6 +857,54 @@ int nbk_tree_query_ex(const nbk_tree *tree, const float *q_aos, uint64_t m, int 
         uploader.reset();
         staged.reset();
         cleanup();
+    });
+}
+
+int nbk_scan_block(const float *x, const float *y, const float *z, const uint32_t *idx, uint64_t n,
+                   const float *q_aos, uint64_t m, int k, int periodic, float box_size, int flags,
+                   float *out_dist, uint32_t *out_idx, int device) {
+    return guarded([&] {
+        if (k <= 0) throw Error(NBK_ERR_INVALID, "k must be positive integer");
+        if (n % 8 != 0) throw Error(NBK_ERR_INVALID, "block_size must be a multiple of 8.");
+        if (n > 0xFFFFFFFFull) throw Error(NBK_ERR_INVALID, "More than uint32_t points are not supported.");
+        if (flags & ~NBK_QUERY_SQUARED) throw Error(NBK_ERR_INVALID, "unknown query flag");
+        if (m == 0) return;
+        if ((n && (!x || !y || !z || !idx)) || !q_aos || !out_dist || !out_idx) throw Error(NBK_ERR_INVALID, "null argument");
+        require_sm100(device);
+        DeviceGuard guard(device);
+        cudaStream_t stream = nullptr;
+        // the block in the tree's tile layout {x[8], y[8], z[8], idx[8]}
+        std::vector<float> tiles(std::max<uint64_t>(n, 8) * 4);
+        for (uint64_t p = 0; p < n; ++p) {
+            float *t = tiles.data() + (p >> 3) * 32 + (p & 7);
+            t[0] = x[p];
+            t[8] = y[p];
+            t[16] = z[p];
+            std::memcpy(&t[24], &idx[p], 4);
+        }
+        Scratch scratch(stream);
+        float *d_tiles = scratch.get<float>(tiles.size());
+        float *d_q = scratch.get<float>(m * 3);
+        float *d_d = scratch.get<float>(m * (uint64_t)k);
+        uint32_t *d_i = scratch.get<uint32_t>(m * (uint64_t)k);
+        NBK_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * 4, cudaMemcpyHostToDevice, stream));
+        NBK_CUDA(cudaMemcpyAsync(d_q, q_aos, m * 12, cudaMemcpyHostToDevice, stream));
+        QueryTree qt{};
+        qt.nodes = nullptr;
+        qt.tiles = reinterpret_cast<const float4 *>(d_tiles);
+        qt.periodic = periodic != 0;
+        qt.box = periodic ? box_size : 0.0f;
+        QueryBatch qb{d_q, nullptr, m, k, flags, d_d, d_i, nullptr, 0u};
+        if (k > kMaxSharedK) {
+            const uint64_t cols = align_up(m, kQueryThreads);
+            qb.gheap = scratch.get<unsigned long long>(cols * (uint64_t)k);
+            qb.gcolumns = (uint32_t)cols;
+        }
+        if (qt.periodic) dispatch_scan_block<true>(qt, (uint32_t)n, qb, stream);
+        else dispatch_scan_block<false>(qt, (uint32_t)n, qb, stream);
+        NBK_CUDA(cudaMemcpyAsync(out_dist, d_d, m * (uint64_t)k * 4, cudaMemcpyDeviceToHost, stream));
+        NBK_CUDA(cudaMemcpyAsync(out_idx, d_i, m * (uint64_t)k * 4, cudaMemcpyDeviceToHost, stream));
+        NBK_CUDA(cudaStreamSynchronize(stream));
     });
 }
 
@@ -820,7 +953,6 @@ int nbk_tree_stats(const nbk_tree *tree, const float *q_aos, uint64_t m, int k, 
     return guarded([&] {
         if (!tree || !out3) throw Error(NBK_ERR_INVALID, "null argument");
         if (k <= 0) throw Error(NBK_ERR_INVALID, "k must be positive integer");
-        if (k > kStatsMaxK) throw Error(NBK_ERR_INVALID, "k > 64 is not supported by this build");
         out3[0] = out3[1] = out3[2] = 0;
         if (m == 0) return;
         DeviceGuard guard(tree->device);
@@ -828,12 +960,14 @@ int nbk_tree_stats(const nbk_tree *tree, const float *q_aos, uint64_t m, int k, 
         Scratch scratch(stream);
         float *d_q = scratch.get<float>(m * 3);
         unsigned long long *d_out = scratch.get<unsigned long long>(3);
+        // k > 64: the replace-top queue of every query lives in a global scratch row
+        float *d_best = k > kStatsMaxK ? scratch.get<float>(m * (uint64_t)k) : nullptr;
         NBK_CUDA(cudaMemcpyAsync(d_q, q_aos, m * 12, cudaMemcpyHostToDevice, stream));
         NBK_CUDA(cudaMemsetAsync(d_out, 0, 24, stream));
         QueryTree qt = tree->query_view(periodic, box_size);
         unsigned grid = (unsigned)div_up(m, 128);
-        if (qt.periodic) stats_kernel<true><<<grid, 128, 0, stream>>>(qt, d_q, m, k, d_out);
-        else stats_kernel<false><<<grid, 128, 0, stream>>>(qt, d_q, m, k, d_out);
+        if (qt.periodic) stats_kernel<true><<<grid, 128, 0, stream>>>(qt, d_q, m, k, d_best, d_out);
+        else stats_kernel<false><<<grid, 128, 0, stream>>>(qt, d_q, m, k, d_best, d_out);
         NBK_LAUNCHED();
         unsigned long long h[3];
         NBK_CUDA(cudaMemcpyAsync(h, d_out, 24, cudaMemcpyDeviceToHost, stream));
@@ -858,7 +992,7 @@ nbk_tree *nbk_tree_alloc_replica(const nbk_tree_meta *meta, int device, int *sta
         DeviceGuard guard(device);
         ArenaLayout l = arena_layout(meta->n_padded, meta->n_nodes);
         if (meta->arena_bytes != l.total) throw Error(NBK_ERR_INVALID, "tree meta does not match this library's arena layout");
-        out = alloc_tree(*meta, device).release();
+        out = alloc_tree(*meta, nullptr).release();
     });
     if (status) *status = st;
     return out;
@@ -872,7 +1006,7 @@ nbk_tree *nbk_tree_clone_to_device(const nbk_tree *tree, int device, int *status
         std::unique_ptr<nbk_tree> copy;
         {
             DeviceGuard guard(device);
-            copy = alloc_tree(tree->meta, device);
+            copy = alloc_tree(tree->meta, nullptr);
             NBK_CUDA(cudaDeviceSynchronize());
         }
         DeviceGuard guard(tree->device);
@@ -908,14 +1042,35 @@ int nbk_profile_read(int section, double *total_ms, uint64_t *count) {
     });
 }
 
-void *nbk_device_alloc(uint64_t bytes) {
+void *nbk_device_alloc(uint64_t bytes) { return nbk_device_alloc_on(-1, bytes); }
+
+void *nbk_device_alloc_on(int device, uint64_t bytes) {
     void *p = nullptr;
-    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
-    if (e != cudaSuccess) {
-        g_error = std::string("cudaMalloc failed: ") + cudaGetErrorString(e);
-        return nullptr;
+    int st = guarded([&] {
+        DeviceGuard guard(device);
+        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            throw Error(NBK_ERR_NOMEM, std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+        }
+    });
+    return st == NBK_OK ? p : nullptr;
+}
+
+int nbk_pointer_device(const void *ptr) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
     }
-    return p;
+    return (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) ? attr.device : -1;
+}
+
+int nbk_host_path_stats(uint64_t *out4) {
+    return guarded([&] {
+        if (!out4) throw Error(NBK_ERR_INVALID, "null argument");
+        for (int i = 0; i < 4; ++i) out4[i] = g_host_path[i].load();
+    });
 }
 
 void nbk_device_free(void *ptr) {
@@ -930,7 +1085,12 @@ int nbk_device_copy(void *dst, const void *src, uint64_t bytes, int kind) {
 }
 
 int nbk_device_zero(void *dst, uint64_t bytes) {
-    return guarded([&] { NBK_CUDA(cudaMemset(dst, 0, bytes)); });
+    // complete on return: work the caller enqueues afterwards on ANY stream (non-blocking ones included)
+    // sees the zeros
+    return guarded([&] {
+        NBK_CUDA(cudaMemsetAsync(dst, 0, bytes, nullptr));
+        NBK_CUDA(cudaStreamSynchronize(nullptr));
+    });
 }
 
 void *nbk_host_alloc(uint64_t bytes) {

@@ -103,7 +103,7 @@ class PyKDTree : public wenda::kdtree::KDTree {
     int device() const noexcept { return nbk_tree_device(handle_); }
 
     std::pair<py::array_t<float>, py::array_t<uint32_t>>
-    query(py::array_t<float, py::array::c_style | py::array::forcecast> points, int k, int workers) {
+    query(py::array_t<float, py::array::c_style | py::array::forcecast> points, int k, int workers, bool squared) {
         (void)workers; // the batch runs on the GPU; kept for call compatibility (pybind.cpp:210)
         if (k <= 0) throw std::runtime_error("k must be positive integer"); // pybind.cpp:92-94
         require_n_by_3(points);
@@ -121,7 +121,8 @@ class PyKDTree : public wenda::kdtree::KDTree {
             int status;
             {
                 py::gil_scoped_release nogil;
-                status = nbk_tree_query(handle_, q + begin * 3, cnt, k, od + begin * k, oi + begin * k);
+                status = nbk_tree_query_ex2(handle_, q + begin * 3, cnt, k, -1, 0.0f, squared ? NBK_QUERY_SQUARED : 0,
+                                            od + begin * k, oi + begin * k);
             }
             if (status != NBK_OK) throw std::runtime_error(nbk_last_error());
             if (PyErr_CheckSignals() != 0) throw py::error_already_set();
@@ -130,12 +131,13 @@ class PyKDTree : public wenda::kdtree::KDTree {
     }
 
     // device buffers in, device buffers out, enqueued on `stream` (no synchronisation)
-    void query_device(uintptr_t d_q, uint64_t m, int k, uintptr_t d_dist, uintptr_t d_idx, uintptr_t stream) {
+    void query_device(uintptr_t d_q, uint64_t m, int k, uintptr_t d_dist, uintptr_t d_idx, uintptr_t stream,
+                      bool squared) {
         if (k <= 0) throw std::runtime_error("k must be positive integer");
         py::gil_scoped_release nogil;
-        check(nbk_tree_query_device(handle_, reinterpret_cast<const float *>(d_q), m, k,
-                                    reinterpret_cast<float *>(d_dist), reinterpret_cast<uint32_t *>(d_idx),
-                                    reinterpret_cast<void *>(stream)));
+        check(nbk_tree_query_device_ex(handle_, reinterpret_cast<const float *>(d_q), m, k, -1, 0.0f,
+                                       squared ? NBK_QUERY_SQUARED : 0, reinterpret_cast<float *>(d_dist),
+                                       reinterpret_cast<uint32_t *>(d_idx), reinterpret_cast<void *>(stream)));
     }
 
     // numpy.histogram(dist[:, k-1], edges) for every k in ks without materialising the rows
@@ -210,7 +212,10 @@ PYBIND11_MODULE(_impl, m) {
              py::arg("stream") = 0)
         .def(py::init(&PyKDTree::from_points), py::arg("points"), py::arg("leafsize") = 64,
              py::arg("max_threads") = -1, py::arg("boxsize") = std::nullopt, py::arg("device") = -1)
-        .def("query", &PyKDTree::query, py::arg("points"), py::arg("k") = 1, py::arg("workers") = 1)
+        // (squared: extension, SURVEY.md 8f-4 `return_squared`; the reference's three arguments keep their
+        // names, order and defaults)
+        .def("query", &PyKDTree::query, py::arg("points"), py::arg("k") = 1, py::arg("workers") = 1,
+             py::arg("squared") = false)
         .def_property_readonly("n", &PyKDTree::num_points)
         .def_property_readonly("size", &PyKDTree::num_nodes)
         .def_property_readonly("periodic", &PyKDTree::periodic)
@@ -220,7 +225,8 @@ PYBIND11_MODULE(_impl, m) {
         .def_property_readonly("_handle", &PyKDTree::raw_handle)
         .def("_nodes_bytes", &PyKDTree::nodes_array)
         .def("_stats", &PyKDTree::stats, py::arg("points"), py::arg("k") = 1)
-        .def("_query_device", &PyKDTree::query_device)
+        .def("_query_device", &PyKDTree::query_device, py::arg("d_q"), py::arg("m"), py::arg("k"), py::arg("d_dist"),
+             py::arg("d_idx"), py::arg("stream") = 0, py::arg("squared") = false)
         .def("_knn_cdf", &PyKDTree::knn_cdf, py::arg("points"), py::arg("ks"), py::arg("edges"))
         .def("_knn_cdf_device", &PyKDTree::knn_cdf_device);
 }

@@ -344,12 +344,8 @@ inline uint64_t build_select(td::TopPlan const &plan, uint64_t n_padded, int lea
     args.nodes = arena.nodes;
     args.tiles = arena.tiles;
     args.error = d_err;
-    static const bool attr_set = [] {
-        NBK_CUDA(cudaFuncSetAttribute(bottom_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)kBottomSmem));
-        return true;
-    }();
-    (void)attr_set;
+    // function attributes are per device: set it on whichever device this build runs on
+    NBK_CUDA(cudaFuncSetAttribute(bottom_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBottomSmem));
     bottom_kernel<<<args.nseg, kBotThreads, kBottomSmem, stream>>>(args);
     NBK_LAUNCHED();
     if (trace) NBK_CUDA(cudaEventRecord(ev[2], stream));

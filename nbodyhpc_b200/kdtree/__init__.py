@@ -13,7 +13,9 @@ Extensions beyond the reference, all opt-in:
   ``__cuda_array_interface__``);
 * ``query_cdf`` -- histograms of the k-th neighbour distance without materialising the ``(M, k)``
   rows (the kNN-CDF use case);
-* N-d query arrays are reshaped as the reference evidently intended (its own reshape raises).
+* N-d query arrays are reshaped as the reference evidently intended (its own reshape raises);
+* ``query(..., return_squared=True)`` returns the squared distances the search ranks by (no ``sqrt``);
+* any ``k`` is accepted, like the reference's queue (k > 64 keeps the candidates in device memory).
 """
 from __future__ import annotations
 
@@ -60,12 +62,12 @@ class DeviceArray:
     """A result left on the device for non-torch callers: owns the memory, exposes
     ``__cuda_array_interface__`` (cupy.asarray / numba.cuda.as_cuda_array / torch.as_tensor accept it)."""
 
-    def __init__(self, shape, dtype):
+    def __init__(self, shape, dtype, device: int = -1):
         from .. import capi
 
         self.shape, self.dtype = tuple(shape), np.dtype(dtype)
         self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
-        self._ptr = capi.device_alloc(self.nbytes)
+        self._ptr = capi.device_alloc(self.nbytes, device)  # on the tree's GPU, not the thread's current one
 
     @property
     def __cuda_array_interface__(self):
@@ -121,6 +123,14 @@ class KDTree(cKDTree):
             ptr, shape = _device_view(points, "points")
             if len(shape) != 2 or shape[1] != 3:
                 raise RuntimeError("positions must be a 2D array of shape (N, 3)")
+            if shape[0]:
+                from .. import capi
+
+                where = capi.pointer_device(ptr)
+                if device == -1:
+                    device = where  # the tree is built where its points are
+                elif where != device:
+                    raise RuntimeError(f"points live on GPU {where} but device={device} was requested")
             stream = _current_stream(points)
             super().__init__(ptr, shape[0], leafsize, max_threads, boxsize, device, stream)
         else:
@@ -134,7 +144,7 @@ class KDTree(cKDTree):
         if len(kwargs) > 0:
             warnings.warn("Unrecognized keyword arguments: {}".format(kwargs))
 
-    def _query_sharded(self, points: np.ndarray, k: int):
+    def _query_sharded(self, points: np.ndarray, k: int, squared: bool = False):
         """Contiguous chunks of the batch, one per replica, answered concurrently."""
         from concurrent.futures import ThreadPoolExecutor
 
@@ -151,7 +161,7 @@ class KDTree(cKDTree):
         def run(rank):
             b, e = shard_range(m, rank, world)
             if e > b:
-                self._shards[rank].query(points[b:e], k, out=(dist[b:e], idx[b:e]))
+                self._shards[rank].query(points[b:e], k, out=(dist[b:e], idx[b:e]), squared=squared)
 
         with ThreadPoolExecutor(max_workers=world) as pool:
             list(pool.map(run, range(world)))
@@ -162,12 +172,15 @@ class KDTree(cKDTree):
 
         ``workers`` is accepted for compatibility (the batch is one GPU launch sequence).  Device
         arrays in give device arrays out, enqueued on the caller's current stream.
+        ``return_squared=True`` (extension) skips the final ``sqrt``: the distances are then the float32
+        squared distances of the reference's metric, bit for bit.
         """
+        squared = bool(kwargs.pop("return_squared", False))
         if len(kwargs) > 0:
             warnings.warn("Unrecognized keyword arguments: {}".format(kwargs))
 
         if _is_device_array(points):
-            return self._query_device_array(points, k)
+            return self._query_device_array(points, k, squared)
 
         points = np.asarray(points)
         if points.ndim != 2:
@@ -177,9 +190,9 @@ class KDTree(cKDTree):
             shape = None
 
         if self._shards is not None:
-            distances, indices = self._query_sharded(points, k)
+            distances, indices = self._query_sharded(points, k, squared)
         else:
-            distances, indices = super().query(points, k, workers)
+            distances, indices = super().query(points, k, workers, squared)
 
         if shape is not None:
             # the reference passes (shape[:-1], k) to reshape, which raises TypeError
@@ -189,13 +202,25 @@ class KDTree(cKDTree):
 
         return distances, indices
 
-    def _query_device_array(self, points, k: int):
+    def _check_same_device(self, ptr: int, m: int):
+        """Device arrays are used in place, so they must live on the tree's GPU."""
+        if m == 0:
+            return
+        from .. import capi
+
+        where = capi.pointer_device(ptr)
+        if where != self.device:
+            raise RuntimeError(f"device array lives on GPU {where}, the tree on GPU {self.device}; "
+                               "move the array (or build the tree with device=...)")
+
+    def _query_device_array(self, points, k: int, squared: bool = False):
         if k <= 0:
             raise RuntimeError("k must be positive integer")
         ptr, shape = _device_view(points, "points")
         if len(shape) < 1 or shape[-1] != 3:
             raise RuntimeError("positions must be a 2D array of shape (N, 3)")
         m = int(np.prod(shape[:-1]))
+        self._check_same_device(ptr, m)
         out_shape = shape[:-1] + (k,)
         stream = _current_stream(points)
         if _is_torch(points):
@@ -204,11 +229,11 @@ class KDTree(cKDTree):
             dist = torch.empty(out_shape, dtype=torch.float32, device=points.device)
             idx = torch.empty(out_shape, dtype=torch.int32, device=points.device)  # uint32 bit patterns
             if m:
-                self._query_device(ptr, m, k, dist.data_ptr(), idx.data_ptr(), stream)
+                self._query_device(ptr, m, k, dist.data_ptr(), idx.data_ptr(), stream, squared)
             return dist, idx
-        dist, idx = DeviceArray(out_shape, np.float32), DeviceArray(out_shape, np.uint32)
+        dist, idx = DeviceArray(out_shape, np.float32, self.device), DeviceArray(out_shape, np.uint32, self.device)
         if m:
-            self._query_device(ptr, m, k, dist._ptr, idx._ptr, stream)
+            self._query_device(ptr, m, k, dist._ptr, idx._ptr, stream, squared)
         return dist, idx
 
     def query_cdf(self, points, ks: Sequence[int], bins) -> np.ndarray:
@@ -230,9 +255,11 @@ class KDTree(cKDTree):
             if len(shape) < 1 or shape[-1] != 3:
                 raise RuntimeError("positions must be a 2D array of shape (N, 3)")
             m = int(np.prod(shape[:-1]))
-            d_edges = DeviceArray(edges.shape, np.float32)
+            self._check_same_device(ptr, m)
+            # both helpers complete before they return, so the kernels on the caller's stream see them
+            d_edges = DeviceArray(edges.shape, np.float32, self.device)
             capi.host_to_device(d_edges._ptr, edges)
-            d_counts = DeviceArray((len(ks), len(edges) - 1), np.uint64)
+            d_counts = DeviceArray((len(ks), len(edges) - 1), np.uint64, self.device)
             capi.device_memset(d_counts._ptr, d_counts.nbytes)
             self._knn_cdf_device(ptr, m, ks, d_edges._ptr, len(edges) - 1, d_counts._ptr, _current_stream(points))
             return d_counts.to_host()

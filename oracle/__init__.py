@@ -142,7 +142,8 @@ class Oracle:
                 raise RuntimeError(f"oracle build failed (status {status.value})")
             super().__init__(h, boxsize is not None, 0.0 if boxsize is None else float(boxsize))
 
-        def query(self, q, k: int = 1, workers: int = 1, brute: bool = False, return_stats: bool = False):
+        def query(self, q, k: int = 1, workers: int = 1, brute: bool = False, return_stats: bool = False,
+                  squared: bool = False):
             q = _aos(q)
             if k <= 0:
                 raise RuntimeError("k must be positive integer")
@@ -152,7 +153,8 @@ class Oracle:
             stats = np.zeros(3, np.uint64)
             if workers <= 0:
                 workers = os.cpu_count() or 1
-            self.lib.orc_tree_query(self._h, q.reshape(-1), m, k, workers, int(brute), d.reshape(-1), i.reshape(-1),
+            self.lib.orc_tree_query(self._h, q.reshape(-1), m, k, workers, int(brute) | (2 if squared else 0),
+                                    d.reshape(-1), i.reshape(-1),
                                     stats.ctypes.data_as(C.c_void_p))
             return (d, i, stats) if return_stats else (d, i)
 
@@ -194,6 +196,9 @@ class Reference:
             L.ref_tree_copy_points.argtypes = [C.c_void_p, _f32p, _f32p, _f32p, _u32p]
             L.ref_tree_query.restype = C.c_int
             L.ref_tree_query.argtypes = [C.c_void_p, _f32p, C.c_uint64, C.c_int, C.c_int, _f32p, _u32p, C.c_void_p]
+            L.ref_tree_query_ex.restype = C.c_int
+            L.ref_tree_query_ex.argtypes = [C.c_void_p, _f32p, C.c_uint64, C.c_int, C.c_int, C.c_int, _f32p, _u32p,
+                                            C.c_void_p]
             L.ref_box_distance.restype = C.c_float
             L.ref_box_distance.argtypes = [_f32p, _f32p, C.c_float]
             L.ref_point_distance.restype = C.c_float
@@ -225,14 +230,14 @@ class Reference:
             self.build_seconds = secs.value
             super().__init__(h, boxsize is not None, 0.0 if boxsize is None else float(boxsize))
 
-        def query(self, q, k: int = 1, workers: int = 1, return_stats: bool = False):
+        def query(self, q, k: int = 1, workers: int = 1, return_stats: bool = False, squared: bool = False):
             q = _aos(q)
             m = q.shape[0]
             d = np.empty((m, max(k, 0)), np.float32)
             i = np.empty((m, max(k, 0)), np.uint32)
             stats = np.zeros(3, np.uint64)
-            rc = self.lib.ref_tree_query(self._h, q.reshape(-1), m, k, workers, d.reshape(-1), i.reshape(-1),
-                                         stats.ctypes.data_as(C.c_void_p))
+            rc = self.lib.ref_tree_query_ex(self._h, q.reshape(-1), m, k, workers, int(squared), d.reshape(-1),
+                                            i.reshape(-1), stats.ctypes.data_as(C.c_void_p))
             if rc:
                 raise RuntimeError(self.lib.ref_last_error().decode())
             return (d, i, stats) if return_stats else (d, i)
@@ -241,9 +246,10 @@ class Reference:
 # ------------------------------------------------------------------------------------------------
 # Parity checker
 # ------------------------------------------------------------------------------------------------
-def point_distance(points: np.ndarray, q: np.ndarray, boxsize=None) -> np.ndarray:
+def point_distance(points: np.ndarray, q: np.ndarray, boxsize=None, squared: bool = False) -> np.ndarray:
     """Reference-arithmetic Euclidean distance (float32, FMA-free; kdtree.hpp:22-31,71-84) of
-    every row of ``points`` to the single query ``q`` -- numpy float32 ops round like the C code."""
+    every row of ``points`` to the single query ``q`` -- numpy float32 ops round like the C code.
+    ``squared``: the value before postprocess()."""
     p = np.asarray(points, np.float32)
     q = np.asarray(q, np.float32)
     acc = np.zeros(p.shape[0], np.float32)
@@ -256,7 +262,7 @@ def point_distance(points: np.ndarray, q: np.ndarray, boxsize=None) -> np.ndarra
             dp, dm = d + L, d - L
             t = np.minimum(np.minimum(d * d, dp * dp), dm * dm)
         acc = acc + t
-    return np.sqrt(acc)
+    return acc if squared else np.sqrt(acc)
 
 
 @dataclass
@@ -281,14 +287,16 @@ def _canon(d: np.ndarray, i: np.ndarray):
     return np.take_along_axis(d, order, 1), np.take_along_axis(i, order, 1)
 
 
-def compare_knn(d_test, i_test, d_ref, i_ref, points=None, queries=None, boxsize=None) -> ParityReport:
+def compare_knn(d_test, i_test, d_ref, i_ref, points=None, queries=None, boxsize=None,
+                squared: bool = False) -> ParityReport:
     """Compares a (distances, indices) result with the reference's on the same inputs.
 
     Distances must be bit-equal row by row.  Index rows must be equal, or equal after ordering
     exact ties by index (the reference leaves the order of equal distances unspecified:
     kdtree_opt.hpp:13-18), or differ only in points whose recomputed distance is exactly the k-th
     distance (the reference keeps the first-visited of such points: kdtree_asm_systemv.asm:155-169);
-    the latter needs ``points``/``queries`` for the recomputation.
+    the latter needs ``points``/``queries`` for the recomputation.  ``squared``: both results hold
+    squared distances (the north star's bar: d2 bit-exact), the recomputation then skips the sqrt too.
     """
     d_test = np.asarray(d_test, np.float32)
     d_ref = np.asarray(d_ref, np.float32)
@@ -312,7 +320,7 @@ def compare_knn(d_test, i_test, d_ref, i_ref, points=None, queries=None, boxsize
                 kth = dt[-1]
                 diff = np.setxor1d(it, ir)
                 diff = diff[diff < np.asarray(points).shape[0]]
-                dd = point_distance(np.asarray(points)[diff], np.asarray(queries)[r], boxsize)
+                dd = point_distance(np.asarray(points)[diff], np.asarray(queries)[r], boxsize, squared)
                 inner_t = np.sort(it[dt < kth])
                 inner_r = np.sort(ir[dr < kth])
                 ok = diff.size > 0 and bool((dd.view(np.uint32) == kth.view(np.uint32)).all()) and np.array_equal(inner_t, inner_r)

@@ -350,10 +350,11 @@ static int cmp_pair(const void *a, const void *b) {
     return (l->i > r->i) - (l->i < r->i);
 }
 
-static void finish_row(orc_pair *best, int k, float *out_d, uint32_t *out_i) {
+static void finish_row(orc_pair *best, int k, int squared, float *out_d, uint32_t *out_i) {
     qsort(best, (size_t)k, sizeof(orc_pair), cmp_pair);   /* kdtree.cpp:149-151, canonical ties */
     for (int j = 0; j < k; ++j) {
-        out_d[j] = sqrtf(best[j].d);                      /* postprocess, kdtree.cpp:154-156 */
+        /* postprocess, kdtree.cpp:154-156; squared: the metric's value before it (kdtree.hpp:22-31,71-84) */
+        out_d[j] = squared ? best[j].d : sqrtf(best[j].d);
         out_i[j] = best[j].i;
     }
 }
@@ -389,9 +390,9 @@ static void *run_job(void *arg) {
     for (uint64_t i = job->begin; i < job->end; ++i) {
         float *od = job->out_d + i * (uint64_t)job->k;
         uint32_t *oi = job->out_i + i * (uint64_t)job->k;
-        if (job->brute) {
+        if (job->brute & 1) {
             brute_one(t, job->q + 3 * i, job->k, best);
-            finish_row(best, job->k, od, oi);
+            finish_row(best, job->k, job->brute & 2, od, oi);
             continue;
         }
         orc_search s;
@@ -406,7 +407,7 @@ static void *run_job(void *arg) {
             bounds[2 * d + 1] = t->periodic ? t->box : FLT_MAX;
         }
         compute(&s, t->nodes, bounds);
-        finish_row(best, job->k, od, oi);
+        finish_row(best, job->k, job->brute & 2, od, oi);
         job->stats[0] += s.nodes_visited;
         job->stats[1] += s.nodes_pruned;
         job->stats[2] += s.points_visited;
@@ -416,8 +417,8 @@ static void *run_job(void *arg) {
 }
 
 /* Batched query (PyKDTree::query pybind.cpp:90-189): contiguous chunks of queries per worker like
- * thread_pool::parallelize_loop (thread_pool.hpp:147-183).  brute != 0 => exhaustive scan instead
- * of the tree walk.  stats (optional) receives the summed KDTreeQueryStatistics counters
+ * thread_pool::parallelize_loop (thread_pool.hpp:147-183).  brute & 1 => exhaustive scan instead
+ * of the tree walk; brute & 2 => rows hold squared distances (no postprocess).  stats (optional) receives the summed KDTreeQueryStatistics counters
  * (kdtree.hpp:124-131).  Returns 0 ok, 1 if k <= 0. */
 int orc_tree_query(const orc_tree *t, const float *q_aos, uint64_t m, int k, int workers, int brute,
                    float *out_d, uint32_t *out_i, uint64_t *stats) {

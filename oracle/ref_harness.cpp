@@ -65,7 +65,7 @@ typedef kdt::TournamentTree<result_t, kdt::PairLessFirst> queue_t;
 
 template <typename Distance>
 void query_range(RefTree const &t, Distance const &distance, const float *q, size_t begin,
-                 size_t end, int k, float *out_d, uint32_t *out_i, uint64_t *stats) {
+                 size_t end, int k, bool squared, float *out_d, uint32_t *out_i, uint64_t *stats) {
     std::vector<result_t> result(k);
     uint64_t nv = 0, np = 0, pv = 0;
     for (size_t i = begin; i < end; ++i) {
@@ -76,7 +76,8 @@ void query_range(RefTree const &t, Distance const &distance, const float *q, siz
         search.distances_.copy_values(result.begin());
         std::sort(result.begin(), result.end(), kdt::PairLessFirst{});
         for (int j = 0; j < k; ++j) {
-            out_d[i * k + j] = distance.postprocess(result[j].first);
+            // squared: the Distance functor's value as the search ranks it, before postprocess()
+            out_d[i * k + j] = squared ? result[j].first : distance.postprocess(result[j].first);
             out_i[i * k + j] = result[j].second;
         }
         nv += search.num_nodes_visited;
@@ -171,8 +172,17 @@ void ref_tree_copy_points(void *handle, float *x, float *y, float *z, uint32_t *
 
 // Batched query, threaded like pybind.cpp:164-172.  stats (optional) = {nodes_visited,
 // nodes_pruned, points_visited} summed over all queries.  Returns 0 on success.
+int ref_tree_query_ex(void *handle, const float *q_aos, uint64_t m, int k, int workers, int squared,
+                      float *out_d, uint32_t *out_i, uint64_t *stats);
+
 int ref_tree_query(void *handle, const float *q_aos, uint64_t m, int k, int workers,
                    float *out_d, uint32_t *out_i, uint64_t *stats) {
+    return ref_tree_query_ex(handle, q_aos, m, k, workers, 0, out_d, out_i, stats);
+}
+
+// squared != 0: rows hold the squared distances (postprocess skipped)
+int ref_tree_query_ex(void *handle, const float *q_aos, uint64_t m, int k, int workers, int squared,
+                      float *out_d, uint32_t *out_i, uint64_t *stats) {
     auto &t = *static_cast<RefTree *>(handle);
     if (k <= 0) {
         g_error = "k must be positive integer";
@@ -182,10 +192,10 @@ int ref_tree_query(void *handle, const float *q_aos, uint64_t m, int k, int work
         stats[0] = stats[1] = stats[2] = 0;
     auto run = [&](size_t begin, size_t end) {
         if (t.periodic)
-            query_range(t, kdt::L2PeriodicDistance<float>{t.box}, q_aos, begin, end, k, out_d,
-                        out_i, stats);
+            query_range(t, kdt::L2PeriodicDistance<float>{t.box}, q_aos, begin, end, k, squared != 0,
+                        out_d, out_i, stats);
         else
-            query_range(t, kdt::L2Distance{}, q_aos, begin, end, k, out_d, out_i, stats);
+            query_range(t, kdt::L2Distance{}, q_aos, begin, end, k, squared != 0, out_d, out_i, stats);
     };
     if (workers == 1 || m == 0) {
         run(0, m);

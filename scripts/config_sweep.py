@@ -21,39 +21,15 @@ from nbodyhpc_b200 import capi  # noqa: E402
 DEV = torch.device("cuda", 0)
 
 
+from scripts.synthetic import uniform as _uniform, zeldovich as _zeldovich  # noqa: E402
+
+
 def uniform(n, seed):
-    g = torch.Generator(device=DEV); g.manual_seed(seed)
-    return torch.rand((n, 3), device=DEV, generator=g)
+    return _uniform(n, seed, DEV)
 
 
 def zeldovich(side, seed, rms_cells=1.5, index=-2.0):
-    """Lattice (i+0.5)/side displaced by psi = grad(inverse-laplacian(delta)), delta a Gaussian field
-    with power-law spectrum P(k) ~ k^index, rms displacement `rms_cells` lattice cells; wrapped to [0,1)."""
-    g = torch.Generator(device=DEV); g.manual_seed(seed)
-    k1 = torch.fft.fftfreq(side, d=1.0 / side, device=DEV)
-    kz = torch.fft.rfftfreq(side, d=1.0 / side, device=DEV)
-    k2 = k1[:, None, None] ** 2 + k1[None, :, None] ** 2 + kz[None, None, :] ** 2
-    k2[0, 0, 0] = 1.0
-    amp = k2 ** (index / 4.0)  # sqrt(P(k)), P ~ k^index
-    amp[0, 0, 0] = 0.0
-    re = torch.randn(k2.shape, device=DEV, generator=g)
-    im = torch.randn(k2.shape, device=DEV, generator=g)
-    delta_k = torch.complex(re * amp, im * amp)
-    del re, im, amp
-    pos = torch.empty((side ** 3, 3), device=DEV)
-    lattice = (torch.arange(side, device=DEV, dtype=torch.float32) + 0.5) / side
-    disp = []
-    for axis, kk in enumerate((k1[:, None, None], k1[None, :, None], kz[None, None, :])):
-        psi_k = 1j * kk * delta_k / k2
-        disp.append(torch.fft.irfftn(psi_k, s=(side, side, side)))
-        del psi_k
-    scale = rms_cells / side / torch.sqrt(sum((d ** 2).mean() for d in disp) / 3.0)
-    for axis in range(3):
-        shape = [1, 1, 1]; shape[axis] = side
-        coord = lattice.view(shape) + disp[axis] * scale
-        pos[:, axis] = torch.remainder(coord, 1.0).reshape(-1)
-    pos.clamp_(0.0, 1.0)
-    return pos
+    return _zeldovich(side, seed, DEV, rms_cells, index)
 
 
 def d2_torch(p, q, box):

@@ -111,6 +111,21 @@ void span_constructor_and_errors() { // kdtree.cpp:64-108
     CHECK(threw);
 }
 
+void any_k_and_position_helper() { // kdtree.cpp:64-90 (make_position_and_indices), :133-141 (any k)
+    auto pts = wk::fill_random_positions(5000, 9);
+    auto soa = wk::make_position_and_indices(tcb::span<const std::array<float, 3>>(pts.data(), pts.size()), 8);
+    CHECK(soa.size() == 5000 && soa.indices_[4999] == 4999);
+    const std::array<float, 3> query = {0.3f, 0.6f, 0.9f};
+    for (size_t k : {65u, 200u}) {
+        auto expected = scan_all(soa, query, k, wk::L2Distance{});
+        wk::KDTree tree(wk::make_position_and_indices(tcb::span<const std::array<float, 3>>(pts.data(), pts.size()), 8));
+        auto result = tree.find_closest(query, k, wk::L2Distance{});
+        CHECK(result.size() == k && result == expected);
+        const wk::L2PeriodicDistance<float> periodic{1.0f};
+        CHECK(tree.find_closest(query, k, periodic) == scan_all(soa, query, k, periodic));
+    }
+}
+
 } // namespace
 
 int main() {
@@ -120,6 +135,7 @@ int main() {
         build_and_find_nearest_periodic(n);
     }
     span_constructor_and_errors();
+    any_k_and_position_helper();
     std::printf(failures ? "%d check(s) failed\n" : "all checks passed\n", failures);
     return failures;
 }

@@ -125,3 +125,29 @@ def test_cpp_fixture_generators_match_the_reference(native):
     # the CLI's layout (main.cpp:14-35): counter {i}, lanes 0..2 -- in (0, 1], deterministic
     a, b = _impl._fill_random_positions(1000, 42), _impl._fill_random_positions(1000, 42)
     assert np.array_equal(a, b) and a.min() > 0.0 and a.max() <= 1.0 and len(np.unique(a)) > 2990
+
+
+def test_cpp_containers_and_helpers_host_only(native, tmp_path):
+    """tests/cpp/test_containers.cpp: PositionAndIndexArray proxy/random-access iterators under STL and
+    ranges algorithms, OffsetRangeContainerWrapper, make_position_and_indices, <span.hpp> -- the parts of
+    the reference's public headers (position_array.hpp:26-161,273-352; kdtree_utils.hpp:117-118;
+    kdtree.hpp:11) that need no device."""
+    libdir = os.path.join(ROOT, "nbodyhpc_b200", "lib")
+    exe = str(tmp_path / "test_containers")
+    subprocess.run(["g++", "-O1", "-std=c++20", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "test_containers.cpp"), "-o", exe, "-L", libdir, "-lnbk",
+                    f"-Wl,-rpath,{libdir}"], check=True, timeout=300)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "all checks passed" in out.stdout, out.stdout + out.stderr
+
+
+def test_query_flag_and_k_validation_without_device(native):
+    """Argument errors come before any device work and use the reference's wording."""
+    q = np.zeros((3, 3), np.float32)
+    with pytest.raises(native.NbkError, match="k must be positive integer"):
+        native.scan_block(q[:0, 0], q[:0, 1], q[:0, 2], np.zeros(0, np.uint32), q, 0)
+    with pytest.raises(native.NbkError, match="block_size must be a multiple of 8."):
+        native.scan_block(q[:, 0], q[:, 1], q[:, 2], np.zeros(3, np.uint32), q, 1)
+    stats = native.host_path_stats()
+    assert set(stats) == {"staged_downloads", "direct_downloads", "staged_uploads", "direct_uploads"}
+    assert native.pointer_device(q.ctypes.data) == -1

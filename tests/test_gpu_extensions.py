@@ -52,8 +52,8 @@ def test_knn_cdf_edge_semantics(gpu):
     assert counts[0, 0] == len(q) and counts[1].sum() == len(q)
     with pytest.raises(gpu.NbkError, match="distinct"):
         tree.knn_cdf(q, [2, 2], edges)
-    with pytest.raises(gpu.NbkError, match="k > 64"):
-        tree.knn_cdf(q, [65], edges)
+    with pytest.raises(gpu.NbkError, match="k must be positive integer"):
+        tree.knn_cdf(q, [0], edges)
     with pytest.raises(gpu.NbkError, match="monotonically"):
         tree.knn_cdf(q, [1], np.array([0.0, 0.2, 0.1], np.float32))
 
