@@ -25,9 +25,14 @@ inline std::atomic<uint64_t> g_host_path[4];
 
 class PinnedRing { // one per device, allocated on first use; a staged call holds it for its duration
   public:
-    static constexpr int kSlots = 12; // [0, kUploadSlots): uploads, the rest: downloads
-    static constexpr int kUploadSlots = 4;
-    static constexpr size_t kSlotBytes = (size_t)32 << 20;
+#ifndef NBK_RING_SLOT_MB
+#define NBK_RING_SLOT_MB 32 // measured: 16 MB slots with 16 threads were slower (0.235 s vs 0.185 s per 10^8 x 8 rows)
+#endif
+    // 384 MB of pinned memory per device.  A slot is the unit one host thread copies, so the number of
+    // download slots bounds how many threads can work on results at once.
+    static constexpr size_t kSlotBytes = (size_t)NBK_RING_SLOT_MB << 20;
+    static constexpr int kSlots = (int)(((size_t)384 << 20) / kSlotBytes); // [0, kUploadSlots): uploads, the rest: downloads
+    static constexpr int kUploadSlots = kSlots / 6;
     static constexpr int kMaxDevices = 64;
     // Blocks while another call on the same device is staging (the transfers of both would share the
     // same PCIe link anyway); calls on different devices -- KDTree(devices=[...]) runs one host thread

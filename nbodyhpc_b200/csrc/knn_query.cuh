@@ -46,6 +46,9 @@ __device__ __forceinline__ float tile_coord(const float4 *tiles, uint32_t p, int
 #ifndef NBK_QUERY_THREADS
 #define NBK_QUERY_THREADS 128
 #endif
+#ifndef NBK_MERGED_INSERT
+#define NBK_MERGED_INSERT 0 // 1: one insertion site per half tile (measured alternative, see scan_half_tile)
+#endif
 constexpr int kQueryThreads = NBK_QUERY_THREADS;
 constexpr int kQueryWarps = kQueryThreads / 32;
 
@@ -59,18 +62,51 @@ __device__ __forceinline__ uint32_t spread10(uint32_t v) {
     return v;
 }
 
+__device__ __forceinline__ uint32_t morton_key(const float *__restrict__ q_aos, uint64_t i, float lo0, float lo1,
+                                               float lo2, float s0, float s1, float s2) {
+    const float qx = q_aos[3 * i], qy = q_aos[3 * i + 1], qz = q_aos[3 * i + 2];
+    const int cx = min(max((int)((qx - lo0) * s0), 0), 1023);
+    const int cy = min(max((int)((qy - lo1) * s1), 0), 1023);
+    const int cz = min(max((int)((qz - lo2) * s2), 0), 1023);
+    return spread10((uint32_t)cx) | (spread10((uint32_t)cy) << 1) | (spread10((uint32_t)cz) << 2);
+}
+
 __global__ void __launch_bounds__(256)
 morton_keys_kernel(const float *__restrict__ q_aos, uint64_t m, float lo0, float lo1, float lo2,
                    float s0, float s1, float s2, uint32_t *__restrict__ keys,
                    uint32_t *__restrict__ vals) {
     uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= m) return;
-    float qx = q_aos[3 * i], qy = q_aos[3 * i + 1], qz = q_aos[3 * i + 2];
-    int cx = min(max((int)((qx - lo0) * s0), 0), 1023);
-    int cy = min(max((int)((qy - lo1) * s1), 0), 1023);
-    int cz = min(max((int)((qz - lo2) * s2), 0), 1023);
-    keys[i] = spread10((uint32_t)cx) | (spread10((uint32_t)cy) << 1) | (spread10((uint32_t)cz) << 2);
+    keys[i] = morton_key(q_aos, i, lo0, lo1, lo2, s0, s1, s2);
     vals[i] = (uint32_t)i;
+}
+
+// Keys + the digit totals of every ordering pass (rs::sweep_order): 4096 queries per CTA, the
+// histograms privatised in shared memory.
+constexpr int kKeysPerCta = 4096;
+constexpr int kMaxOrderPasses = 4;
+__global__ void __launch_bounds__(256)
+morton_keys_totals_kernel(const float *__restrict__ q_aos, uint64_t m, float lo0, float lo1, float lo2,
+                          float s0, float s1, float s2, int first_bit, int passes,
+                          uint32_t *__restrict__ keys, uint32_t *__restrict__ digit_totals) {
+    __shared__ uint32_t h[kMaxOrderPasses][256];
+    for (int p = 0; p < passes; ++p) h[p][threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t base = (uint64_t)blockIdx.x * kKeysPerCta;
+#pragma unroll 4
+    for (int it = 0; it < kKeysPerCta / 256; ++it) {
+        const uint64_t i = base + it * 256 + threadIdx.x;
+        if (i < m) {
+            const uint32_t key = morton_key(q_aos, i, lo0, lo1, lo2, s0, s1, s2);
+            keys[i] = key;
+            for (int p = 0; p < passes; ++p) atomicAdd(&h[p][(key >> (first_bit + 8 * p)) & 255u], 1u);
+        }
+    }
+    __syncthreads();
+    for (int p = 0; p < passes; ++p) {
+        const uint32_t c = h[p][threadIdx.x];
+        if (c) atomicAdd(&digit_totals[p * 256 + threadIdx.x], c);
+    }
 }
 
 // ---- point distance -------------------------------------------------------------------------------
@@ -341,12 +377,28 @@ __device__ __forceinline__ void scan_half_tile(const float4 *g, float qx, float 
         // ncu shows at 76 % of peak -- the kernel's co-limiter next to instruction issue
         const uint4 I = __ldg(reinterpret_cast<const uint4 *>(g + 6));
         const uint32_t idx[4] = {I.x, I.y, I.z, I.w};
+#if NBK_MERGED_INSERT
+        // ONE insertion site per half tile, fed by a per-lane loop over the lane's candidates (selected
+        // with SEL chains, nothing indexed dynamically): the site runs max-over-lanes(#candidates) times
+        // instead of once per point position at which any lane has a candidate.
+        const float w = top.worst();
+        unsigned m = (d[0] <= w ? 1u : 0u) | (d[1] <= w ? 2u : 0u) | (d[2] <= w ? 4u : 0u) | (d[3] <= w ? 8u : 0u);
+        while (m) {
+            const unsigned low = m & (0u - m);
+            m ^= low;
+            const float dj = low == 1u ? d[0] : (low == 2u ? d[1] : (low == 4u ? d[2] : d[3]));
+            const uint32_t ij = low == 1u ? idx[0] : (low == 2u ? idx[1] : (low == 4u ? idx[2] : idx[3]));
+            const uint32_t chi = __float_as_uint(dj);
+            if (top.beats_worst(chi, ij) && !(dedupe && top.contains(chi, ij, k))) top.insert(chi, ij);
+        }
+#else
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const uint32_t chi = __float_as_uint(d[j]);
             if (top.beats_worst(chi, idx[j]) && !(dedupe && top.contains(chi, idx[j], k)))
                 top.insert(chi, idx[j]);
         }
+#endif
     }
 }
 
@@ -355,9 +407,116 @@ __device__ __forceinline__ void scan_leaf(QueryTree const &t, uint32_t begin, ui
                                           float qy, float qz, float wrap_d2, bool dedupe, int k, Top &top) {
     const float4 *tp = t.tiles + (uint64_t)(begin >> 3) * kTileFloat4;
     const float4 *const te = t.tiles + (uint64_t)(end >> 3) * kTileFloat4;
+#ifdef NBK_PREFETCH_LEAF
+    // all lines of the leaf are requested before the first is used (the scan itself asks for one at a time)
+    for (const float4 *pf = tp + kTileFloat4; pf < te; pf += kTileFloat4)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+#endif
     for (; tp != te; tp += kTileFloat4) {
         scan_half_tile<Top, PERIODIC>(tp, qx, qy, qz, t.box, wrap_d2, dedupe, k, top);
         scan_half_tile<Top, PERIODIC>(tp + 1, qx, qy, qz, t.box, wrap_d2, dedupe, k, top);
+    }
+}
+
+// ---- candidate queue: the scan appends, the warp inserts together ---------------------------------------
+// With insertion inside the scan loop a 44-instruction insertion site runs whenever ANY lane of the warp
+// has a candidate at that point position (ncu, round 1: 138 site executions per warp for 30 insertions
+// per lane, 7 of 32 lanes active).  Here the scan only appends (d2, index) keys that pass the float test
+// against the lane's current k-th distance to a small per-lane queue in shared memory, and the warp then
+// drains all queues together: one insertion site, executed max-over-lanes(queue length) times with most
+// lanes busy.  The k-th distance is stale while a queue fills, so a few candidates are appended that
+// an immediate insertion would have rejected; the exact 64-bit test is repeated at the drain.  In the
+// first (home-leaf) round, where the bound falls fastest, the warp drains after every 8-point tile.
+#ifndef NBK_QUEUE_CAP
+#define NBK_QUEUE_CAP 0 // 0: insert inside the scan loop (no queue)
+#endif
+constexpr int kQueueCap = NBK_QUEUE_CAP;
+
+struct CandQueue { // slot-major like the heaps: queue[slot * blockDim + thread]
+    unsigned long long *col;
+    int cnt;
+    __device__ __forceinline__ void bind(unsigned long long *base) {
+        col = base + threadIdx.x;
+        cnt = 0;
+    }
+    __device__ __forceinline__ void push(uint32_t chi, uint32_t clo) {
+        col[(uint32_t)cnt * kQueryThreads] = ((unsigned long long)chi << 32) | clo;
+        ++cnt;
+    }
+};
+
+template <typename Top>
+__device__ __forceinline__ void drain_own(Top &top, CandQueue &cq, bool dedupe, int k) {
+    while (cq.cnt > 0) {
+        --cq.cnt;
+        const unsigned long long key = cq.col[(uint32_t)cq.cnt * kQueryThreads];
+        const uint32_t chi = (uint32_t)(key >> 32), clo = (uint32_t)key;
+        if (top.beats_worst(chi, clo) && !(dedupe && top.contains(chi, clo, k))) top.insert(chi, clo);
+    }
+}
+
+// all 32 lanes call this together
+template <typename Top>
+__device__ __forceinline__ void drain_warp(Top &top, CandQueue &cq, bool dedupe, int k) {
+    while (__any_sync(0xffffffffu, cq.cnt > 0)) {
+        if (cq.cnt > 0) {
+            --cq.cnt;
+            const unsigned long long key = cq.col[(uint32_t)cq.cnt * kQueryThreads];
+            const uint32_t chi = (uint32_t)(key >> 32), clo = (uint32_t)key;
+            if (top.beats_worst(chi, clo) && !(dedupe && top.contains(chi, clo, k))) top.insert(chi, clo);
+        }
+    }
+}
+
+template <typename Top, bool PERIODIC>
+__device__ __forceinline__ void append_half_tile(const float4 *g, float qx, float qy, float qz, float L,
+                                                 float wrap_d2, float bound, CandQueue &cq) {
+    const float4 X = __ldg(g), Y = __ldg(g + 2), Z = __ldg(g + 4);
+    float d[4];
+    d2x4<false>(X, Y, Z, qx, qy, qz, L, d);
+    if (PERIODIC) {
+        const float dmax = fmaxf(fmaxf(d[0], d[1]), fmaxf(d[2], d[3]));
+        if (dmax >= wrap_d2) {
+            const float4 w = d2x4_wrapped(X, Y, Z, qx, qy, qz, L);
+            d[0] = w.x; d[1] = w.y; d[2] = w.z; d[3] = w.w;
+        }
+    }
+    const float dmin = fminf(fminf(d[0], d[1]), fminf(d[2], d[3]));
+    if (dmin <= bound) {
+        const uint4 I = __ldg(reinterpret_cast<const uint4 *>(g + 6));
+        const uint32_t idx[4] = {I.x, I.y, I.z, I.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (d[j] <= bound) cq.push(__float_as_uint(d[j]), idx[j]); // non-strict: ties are settled at the drain
+    }
+}
+
+// All 32 lanes call this together; lanes without a leaf pass begin == end.  `every_tile`: warp-uniform.
+template <typename Top, bool PERIODIC>
+__device__ __forceinline__ void scan_leaf_queued(QueryTree const &t, uint32_t begin, uint32_t end, float qx, float qy,
+                                                 float qz, float wrap_d2, bool dedupe, bool every_tile, int k,
+                                                 Top &top, CandQueue &cq) {
+    const float4 *tp = t.tiles + (uint64_t)(begin >> 3) * kTileFloat4;
+    const float4 *const te = t.tiles + (uint64_t)(end >> 3) * kTileFloat4;
+    if (every_tile) {
+        while (__any_sync(0xffffffffu, tp != te)) {
+            if (tp != te) {
+                const float bound = top.worst();
+                append_half_tile<Top, PERIODIC>(tp, qx, qy, qz, t.box, wrap_d2, bound, cq);
+                append_half_tile<Top, PERIODIC>(tp + 1, qx, qy, qz, t.box, wrap_d2, bound, cq);
+                tp += kTileFloat4;
+            }
+            drain_warp(top, cq, dedupe, k);
+        }
+    } else {
+        for (; tp != te; tp += kTileFloat4) {
+            if (cq.cnt > kQueueCap - 8) drain_own(top, cq, dedupe, k); // rare: room for one more tile
+            const float bound = top.worst();
+            append_half_tile<Top, PERIODIC>(tp, qx, qy, qz, t.box, wrap_d2, bound, cq);
+            append_half_tile<Top, PERIODIC>(tp + 1, qx, qy, qz, t.box, wrap_d2, bound, cq);
+        }
+        __syncwarp();
+        drain_warp(top, cq, dedupe, k);
     }
 }
 
@@ -401,7 +560,7 @@ __device__ __forceinline__ float min_shifted_root_term(float qx, float qy, float
 
 struct DeferList {
     uint32_t *slots; // sorted-order slots of deferred queries
-    uint32_t *count;
+    uint32_t *count; // [0] entries appended by the fast pass, [1] entries handed out by the general pass
 };
 
 // What one launch answers.  flags: NBK_QUERY_SQUARED -> rows hold d2 instead of sqrt(d2).
@@ -476,6 +635,13 @@ __device__ __forceinline__ void lane_query(QueryTree const &t, QueryBatch const 
     bool done = !valid;
     uint32_t lbeg = 0, lend = 0;
     uint32_t home = kNoNode; // first point of the leaf that was scanned up front
+    constexpr bool kQueued = kQueueCap > 0 && !Top::kShared && !Top::kGlobal;
+    CandQueue cq;
+    if (kQueued) {
+        extern __shared__ unsigned long long queue_smem[];
+        cq.bind(queue_smem);
+    }
+    bool first_round = !IMAGES; // the home-leaf round of the fast pass
 
     if (IMAGES && carry) {
         if (valid) top.load_row(qid, k, a.out_d, a.out_i);
@@ -560,13 +726,22 @@ __device__ __forceinline__ void lane_query(QueryTree const &t, QueryBatch const 
             const float ft = __fmul_rn(w, w);
             const float f0 = dim == 0 ? ft : t0, f1 = dim == 1 ? ft : t1, f2 = dim == 2 ? ft : t2;
             // non-strict: an equal-distance point with a smaller index must still be found
-            if (__fadd_rn(__fadd_rn(f0, f1), f2) <= top.worst())
+            if (__fadd_rn(__fadd_rn(f0, f1), f2) <= top.worst()) {
                 stack[sp++] = make_float4(f0, f1, f2, __uint_as_float(far));
+#ifdef NBK_PREFETCH_FAR
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const int4 *>(t.nodes) + far));
+#endif
+            }
             cur = near;
         }
         if (!__any_sync(0xffffffffu, lbeg != lend)) break;
         // ---- scan it ------------------------------------------------------------------------------
-        scan_leaf<Top, PERIODIC>(t, lbeg, lend, qx, qy, qz, wrap_d2, IMAGES && img > 0, k, top);
+        if (kQueued) {
+            scan_leaf_queued<Top, PERIODIC>(t, lbeg, lend, qx, qy, qz, wrap_d2, IMAGES && img > 0, first_round, k, top, cq);
+            first_round = false;
+        } else {
+            scan_leaf<Top, PERIODIC>(t, lbeg, lend, qx, qy, qz, wrap_d2, IMAGES && img > 0, k, top);
+        }
         lbeg = lend = 0;
     }
 
@@ -611,11 +786,16 @@ knn_lane_kernel(QueryTree t, QueryBatch a, DeferList defer, CdfArgs cdf) {
     Top top;
     top.bind(TopBind{heap_smem, a.gheap, a.gcolumns});
     if (IMAGES) {
-        // second pass: a persistent grid walks the work list, 32 consecutive entries per warp and turn
-        const uint32_t n = *defer.count;
-        const uint32_t turn = gridDim.x * kQueryThreads;
-        for (uint32_t base = blockIdx.x * kQueryThreads + (threadIdx.x & ~31u); base < n; base += turn) {
-            const uint32_t pos = base + (threadIdx.x & 31u);
+        // second pass: a persistent grid drains the work list, 32 consecutive entries per warp and turn,
+        // handed out by an atomic ticket so that the warps finish together whatever the list length
+        const uint32_t n = defer.count[0];
+        const uint32_t lane = threadIdx.x & 31u;
+        while (true) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&defer.count[1], 32u);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= n) break;
+            const uint32_t pos = base + lane;
             const bool valid = pos < n;
             lane_query<Top, PERIODIC, IMAGES>(t, a, defer, cdf, top, defer.slots[valid ? pos : base], valid);
         }

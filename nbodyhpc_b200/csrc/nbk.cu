@@ -192,7 +192,12 @@ std::unique_ptr<nbk_tree> finish_build(uint64_t n, uint64_t n_padded, int leaf_s
         const char *v = std::getenv("NBK_BUILD");
         return v && std::string(v) == "sort";
     }();
+    const char *tv = std::getenv("NBK_BUILD_TRACE");
+    const bool trace = tv && tv[0] == '1';
+    const auto host0 = std::chrono::steady_clock::now();
+    auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host0).count(); };
     td::TopPlan top = td::plan_top(n_padded, leaf_size, block_size);
+    if (trace) fprintf(stderr, "[nbk build]   finish_build +%.3f ms: host plan\n", since());
     nbk_tree_meta meta{};
     meta.n_points = n;
     meta.n_padded = n_padded;
@@ -204,6 +209,7 @@ std::unique_ptr<nbk_tree> finish_build(uint64_t n, uint64_t n_padded, int leaf_s
     meta.n_levels = top.n_levels;
     (void)device;
     auto tree = alloc_tree(meta, stream);
+    if (trace) fprintf(stderr, "[nbk build]   finish_build +%.3f ms: arena allocated\n", since());
     uint64_t scratch_bytes = n_padded * 16; // the caller's columns
     if (sort_build) {
         TopologyPlan plan = plan_topology(n_padded, leaf_size, block_size);
@@ -213,14 +219,24 @@ std::unique_ptr<nbk_tree> finish_build(uint64_t n, uint64_t n_padded, int leaf_s
         scratch_bytes += build_select(top, n_padded, leaf_size, block_size, x0, y0, z0, perm, idx0, d_bounds6,
                                       tree->view, stream);
     }
+    if (trace) fprintf(stderr, "[nbk build]   finish_build +%.3f ms: build_select returned\n", since());
     uint32_t b[6];
     NBK_CUDA(cudaMemcpyAsync(b, d_bounds6, sizeof b, cudaMemcpyDeviceToHost, stream));
     NBK_CUDA(cudaStreamSynchronize(stream));
     {
         // A big build's scratch (several times the tree) goes back to the device so that query outputs
         // can use it; a small one stays cached in the pool, which makes the next build allocation-free.
-        size_t free_b = 0, total_b = 0;
-        NBK_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        // (the device's memory size is looked up once: cudaMemGetInfo walks the pools and cost ~9 ms per build)
+        static std::atomic<uint64_t> total_mem[64];
+        int dev_now = 0;
+        NBK_CUDA(cudaGetDevice(&dev_now));
+        uint64_t total_b = dev_now < 64 ? total_mem[dev_now].load() : 0;
+        if (!total_b) {
+            size_t free_b = 0, tb = 0;
+            NBK_CUDA(cudaMemGetInfo(&free_b, &tb));
+            total_b = tb;
+            if (dev_now < 64) total_mem[dev_now].store(total_b);
+        }
         trim_after = scratch_bytes > total_b / 8;
         if (trim_after) {
             cudaMemPool_t pool;
@@ -230,6 +246,7 @@ std::unique_ptr<nbk_tree> finish_build(uint64_t n, uint64_t n_padded, int leaf_s
             NBK_CUDA(cudaMemPoolTrimTo(pool, 0));
         }
     }
+    if (trace) fprintf(stderr, "[nbk build]   finish_build +%.3f ms: pool policy done\n", since());
     for (int d = 0; d < 3; ++d) {
         bool empty = b[d] == 0xFFFFFFFFu && b[3 + d] == 0u;
         uint32_t lo = ordered_to_float(b[d]), hi = ordered_to_float(b[3 + d]);
@@ -258,10 +275,14 @@ std::unique_ptr<nbk_tree> build_from_device_aos(const float *d_aos, uint64_t n, 
     check_build_args(n_padded, block_size, false);
     bool trim_after = false;
     std::unique_ptr<nbk_tree> tree;
+    const char *tv = std::getenv("NBK_BUILD_TRACE");
+    const bool trace = tv && tv[0] == '1';
+    auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host0).count(); };
     {
         Scratch scratch(stream);
         uint64_t cols = std::max<uint64_t>(n_padded, 1);
         scratch.reserve(4 * Scratch::padded(cols * 4) + 256);
+        if (trace) fprintf(stderr, "[nbk build] +%.3f ms: column block reserved\n", since());
         float *x0 = scratch.get<float>(cols), *y0 = scratch.get<float>(cols), *z0 = scratch.get<float>(cols);
         uint32_t *perm = scratch.get<uint32_t>(cols);
         uint32_t *aux = scratch.get<uint32_t>(8); // [0] flags, [1..6] bounds
@@ -275,6 +296,7 @@ std::unique_ptr<nbk_tree> build_from_device_aos(const float *d_aos, uint64_t n, 
         uint32_t flags = 0;
         NBK_CUDA(cudaMemcpyAsync(&flags, aux, 4, cudaMemcpyDeviceToHost, stream));
         NBK_CUDA(cudaStreamSynchronize(stream));
+        if (trace) fprintf(stderr, "[nbk build] +%.3f ms: ingest done\n", since());
         if (flags & 1u) // pybind.cpp:42-46
             throw Error(NBK_ERR_INVALID, "When using periodic boundary conditions, all points must be "
                                          "within the box (0 <= x <= box_size).");
@@ -338,6 +360,8 @@ template <typename Top, bool P>
 void launch_lane(QueryTree const &qt, QueryBatch const &qb, DeferList defer, CdfArgs cdf, cudaStream_t stream) {
     unsigned grid = (unsigned)div_up(qb.m, kQueryThreads);
     size_t smem = Top::kShared ? (size_t)Top::kSize * kQueryThreads * sizeof(unsigned long long) : 0;
+    if (kQueueCap > 0 && !Top::kShared && !Top::kGlobal)
+        smem = (size_t)kQueueCap * kQueryThreads * sizeof(unsigned long long); // the candidate queues
     auto fast = knn_lane_kernel<Top, P, false>;
     auto general = knn_lane_kernel<Top, P, P>;
     if (smem > 48 * 1024) {
@@ -426,10 +450,6 @@ void query_device(nbk_tree const &tree, const float *d_q, uint64_t m, int k, flo
     if (flags & ~NBK_QUERY_SQUARED) throw Error(NBK_ERR_INVALID, "unknown query flag");
     if (m == 0) return;
     if (m > 0xFFFFFFFFull) throw Error(NBK_ERR_INVALID, "more than 2^32-1 queries per call");
-    Scratch scratch(stream);
-    uint32_t *keys_a = scratch.get<uint32_t>(m), *keys_b = scratch.get<uint32_t>(m);
-    uint32_t *vals_a = scratch.get<uint32_t>(m), *vals_b = scratch.get<uint32_t>(m);
-    uint32_t *work = scratch.get<uint32_t>(rs::sort_workspace_entries<uint32_t>(m));
     // Morton grid over the box (periodic) or the points' bounding box (open)
     float lo[3], scale[3];
     QueryTree qt = tree.query_view(periodic, box_size);
@@ -440,11 +460,6 @@ void query_device(nbk_tree const &tree, const float *d_q, uint64_t m, int k, flo
         lo[d] = l;
         scale[d] = (ext > 0.0f && std::isfinite(ext)) ? 1024.0f / ext : 0.0f;
     }
-    SectionTimer t_order(NBK_SECTION_QUERY_ORDER, stream);
-    morton_keys_kernel<<<(unsigned)div_up(m, 256), 256, 0, stream>>>(d_q, m, lo[0], lo[1], lo[2],
-                                                                   scale[0], scale[1], scale[2],
-                                                                   keys_a, vals_a);
-    NBK_LAUNCHED();
     // the lowest two bits per axis only order queries inside one 1/256-box cell (a leaf spans several
     // cells at any realistic density): three 8-bit passes over bits [6, 30) instead of four
     static const int first_bit = [] {
@@ -452,7 +467,35 @@ void query_device(nbk_tree const &tree, const float *d_q, uint64_t m, int k, flo
         const int b = v ? std::atoi(v) : 6;
         return (b >= 0 && b < 30) ? b : 6;
     }();
-    int where = rs::sort_pairs<uint32_t>(keys_a, vals_a, keys_b, vals_b, m, first_bit, 30, work, stream);
+    // NBK_ORDER=passes selects the three-kernel radix passes (rs::sort_pairs) instead of the single-sweep ones
+    static const bool sweep = [] {
+        const char *v = std::getenv("NBK_ORDER");
+        return !(v && std::string(v) == "passes");
+    }();
+    const int passes = (30 - first_bit + 7) / 8;
+    const bool use_sweep = sweep && m < (1ull << 30); // the look-back words hold 30-bit counts
+    Scratch scratch(stream);
+    uint32_t *keys_a = scratch.get<uint32_t>(m), *keys_b = scratch.get<uint32_t>(m);
+    uint32_t *vals_a = scratch.get<uint32_t>(m), *vals_b = scratch.get<uint32_t>(m);
+    uint32_t *work = scratch.get<uint32_t>(use_sweep ? rs::sweep_workspace_entries(m, passes)
+                                                 : rs::sort_workspace_entries<uint32_t>(m));
+    SectionTimer t_order(NBK_SECTION_QUERY_ORDER, stream);
+    int where;
+    if (use_sweep) {
+        rs::SweepWorkspace w = rs::sweep_workspace(work, m, passes, stream);
+        morton_keys_totals_kernel<<<(unsigned)div_up(m, kKeysPerCta), 256, 0, stream>>>(
+            d_q, m, lo[0], lo[1], lo[2], scale[0], scale[1], scale[2], first_bit, passes, keys_a, w.digit_totals);
+        NBK_LAUNCHED();
+        where = rs::sweep_order(keys_a, vals_a, keys_b, vals_b, m, first_bit, passes, w, stream);
+    } else {
+        morton_keys_kernel<<<(unsigned)div_up(m, 256), 256, 0, stream>>>(d_q, m, lo[0], lo[1], lo[2], scale[0],
+                                                                       scale[1], scale[2], keys_a, vals_a);
+        NBK_LAUNCHED();
+#ifndef NBK_SORT_STABLE
+#define NBK_SORT_STABLE 0
+#endif
+        where = rs::sort_pairs<uint32_t, NBK_SORT_STABLE != 0>(keys_a, vals_a, keys_b, vals_b, m, first_bit, 30, work, stream);
+    }
     const uint32_t *order = where ? vals_b : vals_a;
     t_order.finish();
     SectionTimer t_knn(NBK_SECTION_KNN_KERNEL, stream);
@@ -460,7 +503,7 @@ void query_device(nbk_tree const &tree, const float *d_q, uint64_t m, int k, flo
     if (qt.periodic && !use_packet_kernel()) {
         // the sort's input buffers are free again: reuse one as the deferred-query list
         defer.slots = where ? keys_a : keys_b;
-        defer.count = scratch.get<uint32_t>(1);
+        defer.count = scratch.get<uint32_t>(2);
     }
     QueryBatch qb{d_q, order, m, k, flags, d_out_d, d_out_i, nullptr, 0u};
     uint64_t batch = m;
@@ -473,7 +516,7 @@ void query_device(nbk_tree const &tree, const float *d_q, uint64_t m, int k, flo
     for (uint64_t begin = 0; begin < m; begin += batch) {
         qb.order = order + begin;
         qb.m = std::min(batch, m - begin);
-        if (defer.count) NBK_CUDA(cudaMemsetAsync(defer.count, 0, 4, stream));
+        if (defer.count) NBK_CUDA(cudaMemsetAsync(defer.count, 0, 8, stream));
         if (qt.periodic) dispatch_knn<true>(qt, qb, defer, cdf, stream);
         else dispatch_knn<false>(qt, qb, defer, cdf, stream);
     }

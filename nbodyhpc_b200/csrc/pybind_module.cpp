@@ -2,7 +2,10 @@
 // messages as the reference's kdtree/src/cpp/pybind.cpp:196-216, over the B200 C ABI.
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <optional>
+#include <unordered_map>
+#include <vector>
 
 #include <sys/mman.h>
 
@@ -20,16 +23,79 @@ namespace {
 // Result arrays are allocated by the library and handed to numpy through a capsule, like the
 // reference's (pybind.cpp:103-104,174-188).  2 MB alignment + MADV_HUGEPAGE: a 10^8 x 8 result is
 // 3.2 GB per array, and filling it through 4 KB first-touch faults costs more than the query.
+//
+// Big result buffers are RECYCLED: when numpy drops an array, its buffer (>= 64 MB) goes into a small
+// cache instead of back to the OS, and the next result of the same size takes it.  A fresh 6.4 GB
+// allocation costs ~0.15 s of page faults and zeroing per 10^8-query call -- as much as the whole
+// PCIe transfer -- while memory that has been touched before is filled at copy speed.  The cache holds
+// at most NBK_RESULT_CACHE_MB (default 8192; 0 disables it) and only buffers the caller has released.
+class ResultCache {
+  public:
+    static ResultCache &instance() {
+        static ResultCache *cache = new ResultCache(); // leaked on purpose: arrays may outlive static destruction
+        return *cache;
+    }
+    void *take(size_t alloc) {
+        std::lock_guard<std::mutex> lock(mutex_);
+        for (size_t i = 0; i < idle_.size(); ++i)
+            if (idle_[i].second == alloc) {
+                void *p = idle_[i].first;
+                idle_.erase(idle_.begin() + i);
+                idle_bytes_ -= alloc;
+                return p;
+            }
+        return nullptr;
+    }
+    void remember(void *p, size_t alloc) {
+        std::lock_guard<std::mutex> lock(mutex_);
+        live_[p] = alloc;
+    }
+    void give_back(void *p) {
+        size_t alloc = 0;
+        {
+            std::lock_guard<std::mutex> lock(mutex_);
+            auto it = live_.find(p);
+            if (it != live_.end()) {
+                alloc = it->second;
+                live_.erase(it);
+            }
+            if (alloc >= kMinBytes && idle_bytes_ + alloc <= cap_) {
+                idle_.emplace_back(p, alloc);
+                idle_bytes_ += alloc;
+                return;
+            }
+        }
+        std::free(p);
+    }
+    static constexpr size_t kMinBytes = (size_t)64 << 20;
+
+  private:
+    ResultCache() {
+        const char *v = std::getenv("NBK_RESULT_CACHE_MB");
+        cap_ = (v ? std::strtoull(v, nullptr, 10) : 8192ull) << 20;
+    }
+    std::mutex mutex_;
+    std::vector<std::pair<void *, size_t>> idle_;
+    std::unordered_map<void *, size_t> live_;
+    size_t idle_bytes_ = 0, cap_ = 0;
+};
+
 template <typename T> py::array_t<T> make_result(py::ssize_t rows, py::ssize_t cols) {
     constexpr size_t kHuge = (size_t)2 << 20;
     const size_t bytes = (size_t)rows * (size_t)cols * sizeof(T);
-    const size_t alloc = (std::max<size_t>(bytes, 1) + kHuge - 1) / kHuge * kHuge;
-    void *p = std::aligned_alloc(bytes >= kHuge ? kHuge : 64, bytes >= kHuge ? alloc : (std::max<size_t>(bytes, 1) + 63) / 64 * 64);
-    if (!p) throw std::bad_alloc();
+    const bool big = bytes >= kHuge;
+    const size_t alloc = big ? (bytes + kHuge - 1) / kHuge * kHuge : (std::max<size_t>(bytes, 1) + 63) / 64 * 64;
+    ResultCache &cache = ResultCache::instance();
+    void *p = alloc >= ResultCache::kMinBytes ? cache.take(alloc) : nullptr;
+    if (!p) {
+        p = std::aligned_alloc(big ? kHuge : 64, alloc);
+        if (!p) throw std::bad_alloc();
 #ifdef MADV_HUGEPAGE
-    if (bytes >= kHuge) madvise(p, alloc, MADV_HUGEPAGE);
+        if (big) madvise(p, alloc, MADV_HUGEPAGE);
 #endif
-    py::capsule owner(p, [](void *q) { std::free(q); });
+    }
+    cache.remember(p, alloc);
+    py::capsule owner(p, [](void *q) { ResultCache::instance().give_back(q); });
     return py::array_t<T>({rows, cols}, static_cast<T *>(p), owner);
 }
 
