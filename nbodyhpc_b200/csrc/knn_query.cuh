@@ -407,11 +407,6 @@ __device__ __forceinline__ void scan_leaf(QueryTree const &t, uint32_t begin, ui
                                           float qy, float qz, float wrap_d2, bool dedupe, int k, Top &top) {
     const float4 *tp = t.tiles + (uint64_t)(begin >> 3) * kTileFloat4;
     const float4 *const te = t.tiles + (uint64_t)(end >> 3) * kTileFloat4;
-#ifdef NBK_PREFETCH_LEAF
-    // all lines of the leaf are requested before the first is used (the scan itself asks for one at a time)
-    for (const float4 *pf = tp + kTileFloat4; pf < te; pf += kTileFloat4)
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
-#endif
     for (; tp != te; tp += kTileFloat4) {
         scan_half_tile<Top, PERIODIC>(tp, qx, qy, qz, t.box, wrap_d2, dedupe, k, top);
         scan_half_tile<Top, PERIODIC>(tp + 1, qx, qy, qz, t.box, wrap_d2, dedupe, k, top);
@@ -726,12 +721,8 @@ __device__ __forceinline__ void lane_query(QueryTree const &t, QueryBatch const 
             const float ft = __fmul_rn(w, w);
             const float f0 = dim == 0 ? ft : t0, f1 = dim == 1 ? ft : t1, f2 = dim == 2 ? ft : t2;
             // non-strict: an equal-distance point with a smaller index must still be found
-            if (__fadd_rn(__fadd_rn(f0, f1), f2) <= top.worst()) {
+            if (__fadd_rn(__fadd_rn(f0, f1), f2) <= top.worst())
                 stack[sp++] = make_float4(f0, f1, f2, __uint_as_float(far));
-#ifdef NBK_PREFETCH_FAR
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const int4 *>(t.nodes) + far));
-#endif
-            }
             cur = near;
         }
         if (!__any_sync(0xffffffffu, lbeg != lend)) break;
