@@ -491,19 +491,27 @@ def run_b200_arm(args):
 
             q_np = q.cpu().numpy()
             py_tree = KDTree(make_points(), leafsize=args.leaf, boxsize=1.0)
-            d_np, i_np = py_tree.query(q_np, k=k)  # warm-up (first touch of the staging ring)
+            t0 = time.perf_counter()
+            d_np, i_np = py_tree.query(q_np, k=k)  # the first call: fresh pageable result arrays, staged copies
+            first_s = time.perf_counter() - t0
             same_np = bool(np.array_equal(d_np[:100000], out_d[:100000].cpu().numpy()))
-            del d_np, i_np
+            del d_np, i_np  # a caller that drops its results: the buffers are recycled, page-locked in the background
+            time.sleep(1.5)
             times = []
-            for _ in range(2):
+            for _ in range(3):
                 t0 = time.perf_counter()
                 d_np, i_np = py_tree.query(q_np, k=k)
                 checksum = float(d_np[0, 0])
                 times.append(time.perf_counter() - t0)
                 del d_np, i_np
-            e2e_numpy = {"value": m / min(times), "unit": UNIT, "seconds": times, "matches_device_path": same_np,
-                         "api": "nbodyhpc.kdtree.KDTree.query(numpy (M,3) float32, k) -> fresh numpy (M,k) float32 + "
-                                "uint32; pageable host memory both ways, staged through the library's pinned ring",
+            e2e_numpy = {"value": m / float(np.median(times)), "unit": UNIT, "seconds": times,
+                         "first_call": {"value": m / first_s, "seconds": first_s},
+                         "matches_device_path": same_np,
+                         "api": "nbodyhpc.kdtree.KDTree.query(numpy (M,3) float32, k) -> new numpy (M,k) float32 + uint32 "
+                                "arrays; queries pageable (staged through the library's pinned ring); value = median of 3 "
+                                "calls whose result buffers are recycled from results the caller dropped (page-locked by a "
+                                "background thread, written by the copy engine directly); first_call = fresh pageable "
+                                "result arrays",
                          "host_path": capi.host_path_stats()}
             del py_tree, q_np
 

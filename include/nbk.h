@@ -222,6 +222,10 @@ NBK_API int nbk_device_zero(void *dst, uint64_t bytes);
 NBK_API int nbk_host_path_stats(uint64_t *out4);
 NBK_API void *nbk_host_alloc(uint64_t bytes);
 NBK_API void nbk_host_free(void *ptr);
+/* Page-locks / releases a caller-owned host range (cudaHostRegister, portable) so that the host-buffer entry
+ * points copy to and from it directly.  `device`: a device whose context exists (-1 = current). */
+NBK_API int nbk_host_register(void *ptr, uint64_t bytes, int device);
+NBK_API int nbk_host_unregister(void *ptr);
 
 #ifdef __cplusplus
 }

@@ -26,7 +26,8 @@ SYMBOLS = [
     "nbk_tree_knn_cdf", "nbk_tree_knn_cdf_device",
     "nbk_tree_arena", "nbk_tree_alloc_replica", "nbk_tree_clone_to_device", "nbk_profile_enable", "nbk_profile_read",
     "nbk_device_alloc", "nbk_device_alloc_on", "nbk_pointer_device", "nbk_device_free", "nbk_device_copy",
-    "nbk_device_zero", "nbk_host_path_stats", "nbk_host_alloc", "nbk_host_free",
+    "nbk_device_zero", "nbk_host_path_stats", "nbk_host_alloc", "nbk_host_free", "nbk_host_register",
+    "nbk_host_unregister",
 ]
 
 SECTION_QUERY_ORDER, SECTION_KNN_KERNEL = 0, 1
@@ -106,6 +107,8 @@ def lib() -> C.CDLL:
         L.nbk_host_alloc.restype = vp
         L.nbk_host_alloc.argtypes = [u64]
         L.nbk_host_free.argtypes = [vp]
+        L.nbk_host_register.argtypes = [vp, u64, i32]
+        L.nbk_host_unregister.argtypes = [vp]
         _lib = L
     return _lib
 

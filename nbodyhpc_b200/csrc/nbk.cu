@@ -1149,4 +1149,19 @@ void nbk_host_free(void *ptr) {
     if (ptr) cudaFreeHost(ptr);
 }
 
+int nbk_host_register(void *ptr, uint64_t bytes, int device) {
+    return guarded([&] {
+        if (!ptr || !bytes) throw Error(NBK_ERR_INVALID, "null argument");
+        DeviceGuard guard(device);
+        NBK_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    });
+}
+
+int nbk_host_unregister(void *ptr) {
+    return guarded([&] {
+        if (!ptr) throw Error(NBK_ERR_INVALID, "null argument");
+        NBK_CUDA(cudaHostUnregister(ptr));
+    });
+}
+
 } // extern "C"

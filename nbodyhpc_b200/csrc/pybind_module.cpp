@@ -1,8 +1,11 @@
 // pybind11 module `_impl`: same class, argument names, defaults, property names and error
 // messages as the reference's kdtree/src/cpp/pybind.cpp:196-216, over the B200 C ABI.
 #include <cstdlib>
+#include <atomic>
+#include <condition_variable>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <optional>
 #include <unordered_map>
 #include <vector>
@@ -27,57 +30,105 @@ namespace {
 // Big result buffers are RECYCLED: when numpy drops an array, its buffer (>= 64 MB) goes into a small
 // cache instead of back to the OS, and the next result of the same size takes it.  A fresh 6.4 GB
 // allocation costs ~0.15 s of page faults and zeroing per 10^8-query call -- as much as the whole
-// PCIe transfer -- while memory that has been touched before is filled at copy speed.  The cache holds
-// at most NBK_RESULT_CACHE_MB (default 8192; 0 disables it) and only buffers the caller has released.
+// PCIe transfer -- while memory that has been touched before is filled at copy speed.  On its way into
+// the cache a buffer is also page-locked (cudaHostRegister, by a background thread: pinning 3 GB takes
+// longer than a query), so that a recycled buffer is written by the copy engine directly, like the
+// pinned buffers of bench.py's `e2e` leg, with no staging copy at all.  The cache holds at most
+// NBK_RESULT_CACHE_MB (default 8192; 0 disables it) and only buffers the caller has released;
+// NBK_RESULT_PIN=0 keeps them pageable.
 class ResultCache {
   public:
     static ResultCache &instance() {
         static ResultCache *cache = new ResultCache(); // leaked on purpose: arrays may outlive static destruction
         return *cache;
     }
+    static constexpr size_t kMinBytes = (size_t)64 << 20;
+
     void *take(size_t alloc) {
         std::lock_guard<std::mutex> lock(mutex_);
+        int best = -1;
         for (size_t i = 0; i < idle_.size(); ++i)
-            if (idle_[i].second == alloc) {
-                void *p = idle_[i].first;
-                idle_.erase(idle_.begin() + i);
-                idle_bytes_ -= alloc;
-                return p;
-            }
-        return nullptr;
+            if (idle_[i].alloc == alloc && (best < 0 || (idle_[i].pinned && !idle_[best].pinned))) best = (int)i;
+        if (best < 0) return nullptr;
+        Block b = idle_[best];
+        idle_.erase(idle_.begin() + best);
+        held_bytes_ -= b.alloc;
+        live_[b.p] = b;
+        return b.p;
     }
     void remember(void *p, size_t alloc) {
         std::lock_guard<std::mutex> lock(mutex_);
-        live_[p] = alloc;
+        if (!live_.count(p)) live_[p] = Block{p, alloc, false};
     }
     void give_back(void *p) {
-        size_t alloc = 0;
+        Block b{p, 0, false};
+        bool keep = false, pin = false;
         {
             std::lock_guard<std::mutex> lock(mutex_);
             auto it = live_.find(p);
             if (it != live_.end()) {
-                alloc = it->second;
+                b = it->second;
                 live_.erase(it);
             }
-            if (alloc >= kMinBytes && idle_bytes_ + alloc <= cap_) {
-                idle_.emplace_back(p, alloc);
-                idle_bytes_ += alloc;
-                return;
+            keep = b.alloc >= kMinBytes && held_bytes_ + b.alloc <= cap_;
+            if (keep) {
+                held_bytes_ += b.alloc;
+                pin = pin_enabled_ && !b.pinned;
+                if (pin) to_pin_.push_back(b);
+                else idle_.push_back(b);
             }
         }
-        std::free(p);
+        if (pin) {
+            start_worker();
+            cv_.notify_one();
+        } else if (!keep) {
+            release(b);
+        }
     }
-    static constexpr size_t kMinBytes = (size_t)64 << 20;
+    void set_device(int device) { device_.store(device); }
 
   private:
+    struct Block {
+        void *p;
+        size_t alloc;
+        bool pinned;
+    };
     ResultCache() {
         const char *v = std::getenv("NBK_RESULT_CACHE_MB");
         cap_ = (v ? std::strtoull(v, nullptr, 10) : 8192ull) << 20;
+        const char *pin = std::getenv("NBK_RESULT_PIN");
+        pin_enabled_ = !(pin && pin[0] == '0');
+    }
+    static void release(Block const &b) {
+        if (b.pinned) nbk_host_unregister(b.p);
+        std::free(b.p);
+    }
+    void start_worker() {
+        std::lock_guard<std::mutex> lock(mutex_);
+        if (worker_started_) return;
+        worker_started_ = true;
+        std::thread([this] {
+            while (true) {
+                Block b;
+                {
+                    std::unique_lock<std::mutex> lock(mutex_);
+                    cv_.wait(lock, [&] { return !to_pin_.empty(); });
+                    b = to_pin_.front();
+                    to_pin_.erase(to_pin_.begin());
+                }
+                b.pinned = nbk_host_register(b.p, b.alloc, device_.load()) == NBK_OK;
+                std::lock_guard<std::mutex> lock(mutex_);
+                idle_.push_back(b);
+            }
+        }).detach();
     }
     std::mutex mutex_;
-    std::vector<std::pair<void *, size_t>> idle_;
-    std::unordered_map<void *, size_t> live_;
-    size_t idle_bytes_ = 0, cap_ = 0;
+    std::condition_variable cv_;
+    std::vector<Block> idle_, to_pin_;
+    std::unordered_map<void *, Block> live_;
+    size_t held_bytes_ = 0, cap_ = 0;
+    bool pin_enabled_ = true, worker_started_ = false;
+    std::atomic<int> device_{0};
 };
 
 template <typename T> py::array_t<T> make_result(py::ssize_t rows, py::ssize_t cols) {
@@ -174,6 +225,7 @@ class PyKDTree : public wenda::kdtree::KDTree {
         if (k <= 0) throw std::runtime_error("k must be positive integer"); // pybind.cpp:92-94
         require_n_by_3(points);
         const uint64_t m = static_cast<uint64_t>(points.shape(0));
+        ResultCache::instance().set_device(device());
         py::array_t<float> dist = make_result<float>((py::ssize_t)m, (py::ssize_t)k);
         py::array_t<uint32_t> idx = make_result<uint32_t>((py::ssize_t)m, (py::ssize_t)k);
         const float *q = points.data();

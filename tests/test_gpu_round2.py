@@ -190,3 +190,31 @@ def test_device_arrays_must_live_on_the_trees_device(gpu):
             tree.query(pts[:100].to("cuda:1"), k=2)
         other = KDTree(pts.to("cuda:1"), leafsize=64, boxsize=1.0)  # follows the array's device
         assert other.device == 1
+
+
+def test_python_result_buffers_are_recycled_pinned(gpu):
+    """Result arrays a caller has dropped are kept (page-locked in the background) and back the next result
+    of the same shape: that call then needs no staging copy, and the rows are the same."""
+    import time
+
+    from nbodyhpc_b200.kdtree import KDTree
+
+    pts = philox(200_000, 42)
+    q = np.random.default_rng(5).random((2_200_000, 3), dtype=np.float32)  # 2 x 70 MB of results at k = 8
+    tree = KDTree(pts, leafsize=64, boxsize=1.0)
+    s0 = gpu.host_path_stats()
+    d, i = tree.query(q, k=8)
+    s1 = gpu.host_path_stats()
+    assert s1["staged_downloads"] == s0["staged_downloads"] + 1  # fresh pageable arrays: staged through the ring
+    keep_d, keep_i = d.copy(), i.copy()
+    where = d.ctypes.data
+    del d, i
+    time.sleep(1.0)  # the background thread page-locks the two released buffers
+    d, i = tree.query(q, k=8)
+    s2 = gpu.host_path_stats()
+    assert d.ctypes.data == where or i.ctypes.data == where  # same memory, new arrays
+    assert s2["staged_downloads"] == s1["staged_downloads"] and s2["direct_downloads"] == s1["direct_downloads"]
+    assert np.array_equal(d, keep_d) and np.array_equal(i, keep_i)
+    # results still referenced are never touched by later calls
+    d2, i2 = tree.query(q, k=8)
+    assert d2.ctypes.data != d.ctypes.data and np.array_equal(d2, d) and np.array_equal(d, keep_d)
