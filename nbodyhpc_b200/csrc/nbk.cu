@@ -788,21 +788,24 @@ int nbk_tree_query_ex2(const nbk_tree *tree, const float *q_aos, uint64_t m, int
         if (m == 0) return;
         DeviceGuard guard(tree->device);
         // Up to three slices in flight, one stream each: slice c+2 uploads while slice c+1 computes
-        // and slice c downloads.  A slice is ordered (Morton sort) on its own, so it has to be large
-        // enough that neighbouring queries of a warp still share leaves: 2^24 queries by default.
+        // and slice c downloads.  A slice is ordered (Morton sort) on its own, and the kernel gets slower
+        // per query as slices get smaller (fewer queries per leaf), but the pipeline is bound by the copies
+        // over PCIe (8k bytes of rows per query against ~1 ns of kernel), so that slack is free and small
+        // slices win: the first rows leave after a few hundred microseconds and the last download, which
+        // nothing overlaps, is short.  Measured, 10^8 queries from pinned buffers: k = 8: 2^24-query slices
+        // 0.134 s, 2^23 0.124 s, 2^22 with a 2^19 first slice 0.119 s = 0.84 G queries/s against a PCIe
+        // ceiling of 0.85; k = 4 / 16 / 32: 0.078 / 0.240 / 0.479 s against 0.080 / 0.247 / 0.489 s.
         static const uint64_t slice_cfg = [] {
             const char *v = std::getenv("NBK_HOST_SLICE");
             uint64_t n = v ? std::strtoull(v, nullptr, 10) : 0;
-            return n ? n : (1ull << 24);
+            return n ? n : (1ull << 22);
         }();
-        const uint64_t slice = std::min<uint64_t>(m, slice_cfg);
-        // the first slices are smaller (2^21, 2^22, ...) so that the result download -- the bottleneck of
-        // the pipeline over PCIe -- starts after a few milliseconds instead of after a whole slice
         static const uint64_t first_slice = [] {
             const char *v = std::getenv("NBK_HOST_FIRST_SLICE");
             uint64_t n = v ? std::strtoull(v, nullptr, 10) : 0;
-            return n ? n : (1ull << 21);
+            return n ? n : (1ull << 19);
         }();
+        const uint64_t slice = std::min<uint64_t>(m, slice_cfg);
         const int nbuf = (int)std::min<uint64_t>(3, div_up(m, std::min(slice, first_slice)));
         cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
         float *d_q[3] = {}, *d_d[3] = {};

@@ -1,20 +1,33 @@
-"""End-to-end (host pointers, pinned) query timing at the headline config for the current NBK_HOST_SLICE."""
-import os, sys, time
+"""End-to-end timing of nbk_tree_query with pinned host buffers (what bench.py's `e2e` leg measures), for tuning
+the host pipeline: NBK_HOST_SLICE / NBK_HOST_FIRST_SLICE.
+
+    python scripts/e2e_probe.py [queries] [k]"""
+import json
+import os
+import sys
+import time
+
 import torch
-sys.path.insert(0, ".")
-from nbodyhpc_b200 import capi
-n, m, k = 512 ** 3, 100_000_000, 8
-g = torch.Generator(device="cuda"); g.manual_seed(42)
-pts = torch.rand((n, 3), device="cuda", generator=g)
-tree = capi.Tree.build_device(pts.data_ptr(), n, 64, 1.0, stream=torch.cuda.current_stream().cuda_stream)
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from nbodyhpc_b200 import capi  # noqa: E402
+from scripts.synthetic import uniform  # noqa: E402
+
+m = int(float(sys.argv[1])) if len(sys.argv) > 1 else 100_000_000
+k = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+dev = torch.device("cuda", 0)
+pts = uniform(512 ** 3, 42, dev)
+tree = capi.Tree.build_device(pts.data_ptr(), 512 ** 3, 64, 1.0, stream=torch.cuda.current_stream().cuda_stream)
 del pts
-g.manual_seed(43)
-q = torch.rand((m, 3), device="cuda", generator=g)
-qh = torch.empty((m, 3), dtype=torch.float32, pin_memory=True); qh.copy_(q); del q
-od = torch.empty((m, k), dtype=torch.float32, pin_memory=True)
-oi = torch.empty((m, k), dtype=torch.int32, pin_memory=True)
-for it in range(3):
-    torch.cuda.synchronize(); t0 = time.perf_counter()
-    tree.query_raw(qh.data_ptr(), m, k, od.data_ptr(), oi.data_ptr())
-    dt = time.perf_counter() - t0
-    print(os.environ.get("NBK_HOST_SLICE", "default"), f"iter {it}: {dt*1e3:.1f} ms  {m/dt/1e6:.1f} Mq/s", flush=True)
+q = torch.empty((m, 3), dtype=torch.float32, pin_memory=True)
+q.copy_(uniform(m, 43, dev))
+d = torch.empty((m, k), dtype=torch.float32, pin_memory=True)
+i = torch.empty((m, k), dtype=torch.int32, pin_memory=True)
+tree.query_raw(q.data_ptr(), m, k, d.data_ptr(), i.data_ptr())
+times = []
+for _ in range(4):
+    t0 = time.perf_counter()
+    tree.query_raw(q.data_ptr(), m, k, d.data_ptr(), i.data_ptr())
+    times.append(time.perf_counter() - t0)
+print(json.dumps({"env": {a: b for a, b in os.environ.items() if a.startswith("NBK_HOST")}, "m": m, "k": k,
+                  "seconds": [round(t, 4) for t in times], "gqps_best": round(m / min(times) / 1e9, 4)}), flush=True)
