@@ -478,8 +478,8 @@ def run_b200_arm(args):
         dt = reduce_max(time.perf_counter() - t0)
         e2e = {"value": m_job * e2e_steps / dt, "unit": UNIT, "steps": e2e_steps,
                "h2d_bytes_per_step": m * 12, "d2h_bytes_per_step": m * k * 8,
-               "api": "nbk_tree_query (host pointers, pinned): slices of 2^21..2^24 queries on 3 streams, "
-                      "H2D / kernel / D2H overlapped", "cpu_affinity": numa}
+               "api": "nbk_tree_query (host pointers, pinned): slices of 2^19, 2^20, 2^21, then 2^22 queries on 3 "
+                      "streams, H2D / kernel / D2H overlapped", "cpu_affinity": numa}
         same = bool(torch.equal(od_host[:100000], out_d[:100000].cpu()))
         e2e["matches_device_path"] = same
         del q_host, od_host, oi_host

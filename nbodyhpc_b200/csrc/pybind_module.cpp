@@ -73,7 +73,7 @@ class ResultCache {
             keep = b.alloc >= kMinBytes && held_bytes_ + b.alloc <= cap_;
             if (keep) {
                 held_bytes_ += b.alloc;
-                pin = pin_enabled_ && !b.pinned;
+                pin = pin_enabled_ && !b.pinned && !stopping_.load();
                 if (pin) to_pin_.push_back(b);
                 else idle_.push_back(b);
             }
@@ -107,6 +107,13 @@ class ResultCache {
         std::lock_guard<std::mutex> lock(mutex_);
         if (worker_started_) return;
         worker_started_ = true;
+        // At process exit no registration may be in flight while the CUDA runtime shuts down: this handler is
+        // registered after CUDA's own (it exists by the time a result is recycled), so it runs before it.
+        std::atexit([] {
+            ResultCache &c = ResultCache::instance();
+            c.stopping_.store(true);
+            std::lock_guard<std::mutex> wait_for_registration(c.pinning_);
+        });
         std::thread([this] {
             while (true) {
                 Block b;
@@ -116,13 +123,17 @@ class ResultCache {
                     b = to_pin_.front();
                     to_pin_.erase(to_pin_.begin());
                 }
-                b.pinned = nbk_host_register(b.p, b.alloc, device_.load()) == NBK_OK;
+                {
+                    std::lock_guard<std::mutex> busy(pinning_);
+                    if (!stopping_.load()) b.pinned = nbk_host_register(b.p, b.alloc, device_.load()) == NBK_OK;
+                }
                 std::lock_guard<std::mutex> lock(mutex_);
                 idle_.push_back(b);
             }
         }).detach();
     }
-    std::mutex mutex_;
+    std::mutex mutex_, pinning_;
+    std::atomic<bool> stopping_{false};
     std::condition_variable cv_;
     std::vector<Block> idle_, to_pin_;
     std::unordered_map<void *, Block> live_;
