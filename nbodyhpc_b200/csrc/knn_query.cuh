@@ -357,10 +357,11 @@ template <int K> using HeapK = HeapT<K>;
 // indices are four 16-byte loads from one 128-byte tile.  PERIODIC: a wrapped image can only win on
 // an axis with |p - q| > L/2, i.e. when the open d2 is >= (L/2)^2 = wrap_d2; only then is the
 // 3-image formula evaluated.  `dedupe` is set while a shifted image is searched.
-template <typename Top, bool PERIODIC>
+template <typename Top, bool PERIODIC, bool STAGED = false>
 __device__ __forceinline__ void scan_half_tile(const float4 *g, float qx, float qy, float qz, float L,
                                                float wrap_d2, bool dedupe, int k, Top &top) {
-    const float4 X = __ldg(g), Y = __ldg(g + 2), Z = __ldg(g + 4);
+    // STAGED: g points into shared memory (a leaf staged by a TMA bulk copy, see NBK_STAGE_HOME)
+    const float4 X = STAGED ? g[0] : __ldg(g), Y = STAGED ? g[2] : __ldg(g + 2), Z = STAGED ? g[4] : __ldg(g + 4);
     float d[4];
     d2x4<false>(X, Y, Z, qx, qy, qz, L, d);
     if (PERIODIC) {
@@ -375,7 +376,7 @@ __device__ __forceinline__ void scan_half_tile(const float4 *g, float qx, float 
         // the indices are needed by about one half-tile in five: loading them here (same 128-byte line
         // as the coordinates, an L1 hit) instead of up front takes a quarter off the L1 wavefronts, which
         // ncu shows at 76 % of peak -- the kernel's co-limiter next to instruction issue
-        const uint4 I = __ldg(reinterpret_cast<const uint4 *>(g + 6));
+        const uint4 I = STAGED ? *reinterpret_cast<const uint4 *>(g + 6) : __ldg(reinterpret_cast<const uint4 *>(g + 6));
         const uint32_t idx[4] = {I.x, I.y, I.z, I.w};
 #if NBK_MERGED_INSERT
         // ONE insertion site per half tile, fed by a per-lane loop over the lane's candidates (selected
@@ -515,6 +516,56 @@ __device__ __forceinline__ void scan_leaf_queued(QueryTree const &t, uint32_t be
     }
 }
 
+// ---- measured alternative: the home leaf staged in shared memory by TMA (NBK_STAGE_HOME=1) -------------
+// When all queries of a warp live in the same leaf (one leaf holds ~1.5 warps of queries at the headline
+// density), one elected lane issues ONE bulk copy global -> shared of the leaf's tiles (cp.async.bulk with
+// an mbarrier transaction count), the warp waits on the mbarrier and all 32 lanes scan the staged copy with
+// broadcast shared-memory loads.  Other warps and all later leaves use the global loads.
+#ifndef NBK_STAGE_HOME
+#define NBK_STAGE_HOME 0
+#endif
+constexpr uint32_t kStagePoints = 128;                      // largest leaf that is staged
+constexpr uint32_t kStageBytesPerWarp = kStagePoints * 16;  // tiles: 16 bytes per point
+constexpr size_t kStageSmem = NBK_STAGE_HOME ? (size_t)kQueryWarps * kStageBytesPerWarp + 8 * kQueryWarps : 0;
+
+struct StageBuf {
+    float4 *tiles; // this warp's staging area
+    uint32_t mbar; // shared-memory address of this warp's mbarrier
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void stage_init(StageBuf &sb, unsigned long long *smem) {
+    unsigned char *base = reinterpret_cast<unsigned char *>(smem);
+    const int warp = threadIdx.x >> 5;
+    sb.tiles = reinterpret_cast<float4 *>(base + (size_t)warp * kStageBytesPerWarp);
+    sb.mbar = smem_addr(base + (size_t)kQueryWarps * kStageBytesPerWarp + 8 * warp);
+    if ((threadIdx.x & 31) == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sb.mbar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+}
+
+// one lane: arm the barrier with the byte count, start the bulk copy
+__device__ __forceinline__ void stage_load(StageBuf const &sb, const void *src, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sb.mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(sb.tiles)), "l"(src), "r"(bytes), "r"(sb.mbar)
+                 : "memory");
+}
+
+__device__ __forceinline__ void stage_wait(StageBuf const &sb, uint32_t phase) {
+    uint32_t done = 0, spins = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(sb.mbar), "r"(phase)
+                     : "memory");
+        if (!done && ++spins > (1u << 22)) __trap(); // never hang the device
+    }
+}
+
 // ---- the lane kernel: one query per lane, independent traversal -----------------------------------
 //
 // Pruning bound.  A cell is described by per-axis terms (t0, t1, t2) whose ordered sum
@@ -605,7 +656,8 @@ __device__ __forceinline__ void cdf_accumulate(CdfArgs const &c, int row, uint32
 // One query per lane, all 32 lanes of the warp call this together (`valid` = this lane has a query).
 template <typename Top, bool PERIODIC, bool IMAGES>
 __device__ __forceinline__ void lane_query(QueryTree const &t, QueryBatch const &a, DeferList const &defer,
-                                           CdfArgs const &cdf, Top &top, uint64_t slot, bool valid) {
+                                           CdfArgs const &cdf, Top &top, uint64_t slot, bool valid,
+                                           StageBuf const &stage = StageBuf{nullptr, 0u}) {
     const uint32_t qid = a.order[valid ? slot : a.m - 1];
     const float qx = a.q_aos[3 * (uint64_t)qid], qy = a.q_aos[3 * (uint64_t)qid + 1],
                 qz = a.q_aos[3 * (uint64_t)qid + 2];
@@ -727,7 +779,30 @@ __device__ __forceinline__ void lane_query(QueryTree const &t, QueryBatch const 
         }
         if (!__any_sync(0xffffffffu, lbeg != lend)) break;
         // ---- scan it ------------------------------------------------------------------------------
-        if (kQueued) {
+        constexpr bool kStaged = NBK_STAGE_HOME != 0 && !IMAGES && !Top::kShared && !Top::kGlobal && kQueueCap == 0;
+        if (kStaged && first_round) {
+            first_round = false;
+            // do all queries of the warp live in one (small enough) leaf?
+            const unsigned vm = __ballot_sync(0xffffffffu, valid);
+            const int src = __ffs(vm) - 1;
+            const uint32_t b0 = __shfl_sync(0xffffffffu, lbeg, src), e0 = __shfl_sync(0xffffffffu, lend, src);
+            const bool one_leaf = __all_sync(0xffffffffu, !valid || (lbeg == b0 && lend == e0)) && e0 > b0 &&
+                                  e0 - b0 <= kStagePoints;
+            if (one_leaf) {
+                if ((threadIdx.x & 31) == 0)
+                    stage_load(stage, t.tiles + (uint64_t)(b0 >> 3) * kTileFloat4, (e0 - b0) * 16u);
+                stage_wait(stage, 0u); // one use per kernel: phase 0
+                if (valid) {
+                    const float4 *sp_tile = stage.tiles;
+                    for (uint32_t p = b0; p != e0; p += 8u, sp_tile += kTileFloat4) {
+                        scan_half_tile<Top, PERIODIC, true>(sp_tile, qx, qy, qz, t.box, wrap_d2, false, k, top);
+                        scan_half_tile<Top, PERIODIC, true>(sp_tile + 1, qx, qy, qz, t.box, wrap_d2, false, k, top);
+                    }
+                }
+            } else {
+                scan_leaf<Top, PERIODIC>(t, lbeg, lend, qx, qy, qz, wrap_d2, false, k, top);
+            }
+        } else if (kQueued) {
             scan_leaf_queued<Top, PERIODIC>(t, lbeg, lend, qx, qy, qz, wrap_d2, IMAGES && img > 0, first_round, k, top, cq);
             first_round = false;
         } else {
@@ -794,7 +869,9 @@ knn_lane_kernel(QueryTree t, QueryBatch a, DeferList defer, CdfArgs cdf) {
         const uint64_t slot = (uint64_t)blockIdx.x * kQueryThreads + threadIdx.x;
         const bool valid = slot < a.m;
         if (!__any_sync(0xffffffffu, valid)) return;
-        lane_query<Top, PERIODIC, IMAGES>(t, a, defer, cdf, top, slot, valid);
+        StageBuf stage{nullptr, 0u};
+        if (NBK_STAGE_HOME != 0 && !Top::kShared && !Top::kGlobal && kQueueCap == 0) stage_init(stage, heap_smem);
+        lane_query<Top, PERIODIC, IMAGES>(t, a, defer, cdf, top, slot, valid, stage);
     }
 }
 

@@ -362,6 +362,8 @@ void launch_lane(QueryTree const &qt, QueryBatch const &qb, DeferList defer, Cdf
     size_t smem = Top::kShared ? (size_t)Top::kSize * kQueryThreads * sizeof(unsigned long long) : 0;
     if (kQueueCap > 0 && !Top::kShared && !Top::kGlobal)
         smem = (size_t)kQueueCap * kQueryThreads * sizeof(unsigned long long); // the candidate queues
+    else if (kStageSmem > 0 && !Top::kShared && !Top::kGlobal)
+        smem = kStageSmem; // NBK_STAGE_HOME: one staged leaf + one mbarrier per warp
     auto fast = knn_lane_kernel<Top, P, false>;
     auto general = knn_lane_kernel<Top, P, P>;
     if (smem > 48 * 1024) {
