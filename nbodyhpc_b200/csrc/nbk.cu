@@ -352,6 +352,15 @@ inline bool use_packet_kernel() {
 }
 
 constexpr int kMaxSharedK = 64; // above: heaps in global memory
+// NBK_MAX_SHARED_K (8..64): experiments with the global-memory heap for smaller k
+inline int max_shared_k() {
+    static const int v = [] {
+        const char *e = std::getenv("NBK_MAX_SHARED_K");
+        const int n = e ? std::atoi(e) : kMaxSharedK;
+        return (n >= 8 && n <= kMaxSharedK) ? n : kMaxSharedK;
+    }();
+    return v;
+}
 
 // second (shifted images) pass: a persistent grid over the device-side work list
 constexpr unsigned kImagesGridMax = 148 * 8;
@@ -405,6 +414,10 @@ void launch_knn(QueryTree const &qt, QueryBatch const &qb, DeferList defer, CdfA
 template <bool P>
 void dispatch_knn(QueryTree const &qt, QueryBatch const &qb, DeferList defer, CdfArgs cdf, cudaStream_t stream) {
     const int k = qb.k;
+    if (k > max_shared_k()) {
+        launch_knn<0, P>(qt, qb, defer, cdf, stream);
+        return;
+    }
     if (k <= 1) launch_knn<1, P>(qt, qb, defer, cdf, stream);
     else if (k <= 2) launch_knn<2, P>(qt, qb, defer, cdf, stream);
     else if (k <= 4) launch_knn<4, P>(qt, qb, defer, cdf, stream);
@@ -509,7 +522,7 @@ void query_device(nbk_tree const &tree, const float *d_q, uint64_t m, int k, flo
     }
     QueryBatch qb{d_q, order, m, k, flags, d_out_d, d_out_i, nullptr, 0u};
     uint64_t batch = m;
-    if (k > kMaxSharedK) {
+    if (k > max_shared_k()) {
         const uint64_t cols = global_heap_columns(k);
         qb.gheap = scratch.get<unsigned long long>(cols * (uint64_t)k);
         qb.gcolumns = (uint32_t)cols;
@@ -807,7 +820,9 @@ int nbk_tree_query_ex2(const nbk_tree *tree, const float *q_aos, uint64_t m, int
             uint64_t n = v ? std::strtoull(v, nullptr, 10) : 0;
             return n ? n : (1ull << 19);
         }();
-        const uint64_t slice = std::min<uint64_t>(m, slice_cfg);
+        // wide rows: keep the three in-flight result buffers at <= 1 GB each
+        const uint64_t by_rows = std::max<uint64_t>(1ull << 16, (1ull << 27) / (uint64_t)k);
+        const uint64_t slice = std::min<uint64_t>(m, std::min(slice_cfg, by_rows));
         const int nbuf = (int)std::min<uint64_t>(3, div_up(m, std::min(slice, first_slice)));
         cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
         float *d_q[3] = {}, *d_d[3] = {};
