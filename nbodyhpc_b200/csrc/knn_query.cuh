@@ -192,6 +192,8 @@ template <int K> struct TopK {
     static constexpr int kSize = K;
     static constexpr bool kShared = false;
     static constexpr bool kGlobal = false;
+    static constexpr bool kNeedsIndex = true;
+    static constexpr int kKeyBytes = 8;
     __device__ __forceinline__ void bind(TopBind const &) {}
     // f(j, d2 bits) for every rank j (0 = nearest); any order
     template <typename F> __device__ __forceinline__ void for_each_rank(int k, F &&f) {
@@ -261,6 +263,8 @@ template <int KS> struct HeapT {
     static constexpr int kSize = KS;
     static constexpr bool kShared = KS > 0;
     static constexpr bool kGlobal = KS == 0;
+    static constexpr bool kNeedsIndex = true;
+    static constexpr int kKeyBytes = 8;
     unsigned long long *heap; // this thread's column
     uint32_t stride;
     int n;            // heap size = k
@@ -353,6 +357,101 @@ template <int KS> struct HeapT {
 };
 template <int K> using HeapK = HeapT<K>;
 
+// ---- distance-only containers: the fast pass of the fused kNN-CDF -------------------------------------------
+// The histograms need the k smallest DISTANCES of a query, as a multiset, and nothing else: no indices, and
+// equal distances need no order (inserting a candidate that ties the current worst or not gives the same
+// multiset).  So the keys are the 32-bit d2 patterns: half the shared memory per lane, one compare instead of
+// two per step, no index loads in the leaf scan.  A point must not be met twice (there is nothing to
+// recognise it by), which holds for the fast pass (one image); the boundary pass keeps the (d2, index)
+// containers above.
+template <int K> struct DistTopK { // k <= 8: sorted register list, two min/max per insertion step
+    uint32_t hi[K];
+    static constexpr int kSize = K;
+    static constexpr bool kShared = false;
+    static constexpr bool kGlobal = false;
+    static constexpr bool kNeedsIndex = false;
+    static constexpr int kKeyBytes = 4;
+    __device__ __forceinline__ void bind(TopBind const &) {}
+    __device__ __forceinline__ void init(int k) {
+        const int pad = K - k;
+#pragma unroll
+        for (int j = 0; j < K; ++j) hi[j] = j < pad ? 0u : kFltMaxBits;
+    }
+    __device__ __forceinline__ float worst() const { return __uint_as_float(hi[K - 1]); }
+    __device__ __forceinline__ bool beats_worst(uint32_t chi, uint32_t) const { return chi < hi[K - 1]; }
+    __device__ __forceinline__ bool contains(uint32_t, uint32_t, int) const { return false; }
+    __device__ __forceinline__ void insert(uint32_t chi, uint32_t) {
+        hi[K - 1] = chi;
+#pragma unroll
+        for (int j = K - 1; j > 0; --j) {
+            const uint32_t a = hi[j - 1], b = hi[j];
+            hi[j - 1] = min(a, b);
+            hi[j] = max(a, b);
+        }
+    }
+    template <typename F> __device__ __forceinline__ void for_each_rank(int k, F &&f) {
+        const int pad = K - k;
+#pragma unroll
+        for (int j = 0; j < K; ++j)
+            if (j >= pad) f(j - pad, hi[j]);
+    }
+    __device__ __forceinline__ void write_row(uint32_t, int, bool, float *, uint32_t *) const {} // CDF only
+    __device__ __forceinline__ void load_row(uint32_t, int, const float *, const uint32_t *) {}
+};
+
+template <int KS> struct DistHeapT { // 8 < k <= KS: max-heap of 32-bit keys in shared memory
+    static constexpr int kSize = KS;
+    static constexpr bool kShared = true;
+    static constexpr bool kGlobal = false;
+    static constexpr bool kNeedsIndex = false;
+    static constexpr int kKeyBytes = 4;
+    uint32_t *heap; // this thread's column, heap[slot * blockDim + thread]
+    uint32_t stride;
+    int n;
+    uint32_t root;
+    __device__ __forceinline__ void bind(TopBind const &b) {
+        heap = reinterpret_cast<uint32_t *>(b.smem) + threadIdx.x;
+        stride = blockDim.x;
+    }
+    __device__ __forceinline__ uint32_t &at(int slot) const { return heap[(uint32_t)slot * stride]; }
+    __device__ __forceinline__ void init(int k) {
+        n = k;
+        for (int j = 0; j < n; ++j) at(j) = kFltMaxBits;
+        root = kFltMaxBits;
+    }
+    __device__ __forceinline__ float worst() const { return __uint_as_float(root); }
+    __device__ __forceinline__ bool beats_worst(uint32_t chi, uint32_t) const { return chi < root; }
+    __device__ __forceinline__ bool contains(uint32_t, uint32_t, int) const { return false; }
+    __device__ __forceinline__ void sift_down(uint32_t c, int size) {
+        int i = 0;
+        while (true) {
+            const int l = 2 * i + 1;
+            if (l >= size) break;
+            const int r = l + 1;
+            const uint32_t kl = at(l);
+            const uint32_t kr = r < size ? at(r) : 0u;
+            const bool right = kr > kl;
+            const uint32_t kb = right ? kr : kl;
+            if (kb <= c) break;
+            at(i) = kb;
+            i = right ? r : l;
+        }
+        at(i) = c;
+    }
+    __device__ __forceinline__ void insert(uint32_t chi, uint32_t) {
+        sift_down(chi, n);
+        root = at(0);
+    }
+    template <typename F> __device__ __forceinline__ void for_each_rank(int, F &&f) { // largest first; consumes the heap
+        for (int size = n; size > 0; --size) {
+            f(size - 1, at(0));
+            if (size > 1) sift_down(at(size - 1), size - 1);
+        }
+    }
+    __device__ __forceinline__ void write_row(uint32_t, int, bool, float *, uint32_t *) {} // CDF only
+    __device__ __forceinline__ void load_row(uint32_t, int, const float *, const uint32_t *) {}
+};
+
 // Scans the tiles [begin, end) of one leaf for this lane's query.  Per 4 points: x, y, z and the
 // indices are four 16-byte loads from one 128-byte tile.  PERIODIC: a wrapped image can only win on
 // an axis with |p - q| > L/2, i.e. when the open d2 is >= (L/2)^2 = wrap_d2; only then is the
@@ -376,7 +475,8 @@ __device__ __forceinline__ void scan_half_tile(const float4 *g, float qx, float 
         // the indices are needed by about one half-tile in five: loading them here (same 128-byte line
         // as the coordinates, an L1 hit) instead of up front takes a quarter off the L1 wavefronts, which
         // ncu shows at 76 % of peak -- the kernel's co-limiter next to instruction issue
-        const uint4 I = STAGED ? *reinterpret_cast<const uint4 *>(g + 6) : __ldg(reinterpret_cast<const uint4 *>(g + 6));
+        uint4 I = make_uint4(0u, 0u, 0u, 0u);
+        if (Top::kNeedsIndex) I = STAGED ? *reinterpret_cast<const uint4 *>(g + 6) : __ldg(reinterpret_cast<const uint4 *>(g + 6));
         const uint32_t idx[4] = {I.x, I.y, I.z, I.w};
 #if NBK_MERGED_INSERT
         // ONE insertion site per half tile, fed by a per-lane loop over the lane's candidates (selected

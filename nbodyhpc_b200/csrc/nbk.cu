@@ -365,21 +365,25 @@ inline int max_shared_k() {
 // second (shifted images) pass: a persistent grid over the device-side work list
 constexpr unsigned kImagesGridMax = 148 * 8;
 
-template <typename Top, bool P>
+template <typename Top> constexpr size_t lane_smem() {
+    if (Top::kShared) return (size_t)Top::kSize * kQueryThreads * Top::kKeyBytes;
+    if (kQueueCap > 0 && !Top::kGlobal) return (size_t)kQueueCap * kQueryThreads * sizeof(unsigned long long); // candidate queues
+    if (kStageSmem > 0 && !Top::kGlobal) return kStageSmem; // NBK_STAGE_HOME: one staged leaf + one mbarrier per warp
+    return 0;
+}
+
+// TopFast: container of the first pass; Top: container of the boundary pass (they differ for the kNN-CDF)
+template <typename TopFast, typename Top, bool P>
 void launch_lane(QueryTree const &qt, QueryBatch const &qb, DeferList defer, CdfArgs cdf, cudaStream_t stream) {
     unsigned grid = (unsigned)div_up(qb.m, kQueryThreads);
-    size_t smem = Top::kShared ? (size_t)Top::kSize * kQueryThreads * sizeof(unsigned long long) : 0;
-    if (kQueueCap > 0 && !Top::kShared && !Top::kGlobal)
-        smem = (size_t)kQueueCap * kQueryThreads * sizeof(unsigned long long); // the candidate queues
-    else if (kStageSmem > 0 && !Top::kShared && !Top::kGlobal)
-        smem = kStageSmem; // NBK_STAGE_HOME: one staged leaf + one mbarrier per warp
-    auto fast = knn_lane_kernel<Top, P, false>;
+    constexpr size_t smem_fast = lane_smem<TopFast>(), smem = lane_smem<Top>();
+    auto fast = knn_lane_kernel<TopFast, P, false>;
     auto general = knn_lane_kernel<Top, P, P>;
-    if (smem > 48 * 1024) {
-        NBK_CUDA(cudaFuncSetAttribute(fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem_fast > 48 * 1024)
+        NBK_CUDA(cudaFuncSetAttribute(fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
+    if (smem > 48 * 1024)
         NBK_CUDA(cudaFuncSetAttribute(general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
-    fast<<<grid, kQueryThreads, smem, stream>>>(qt, qb, defer, cdf);
+    fast<<<grid, kQueryThreads, smem_fast, stream>>>(qt, qb, defer, cdf);
     NBK_LAUNCHED();
     if (P) {
         // queries whose search ball reaches through a face of the box (usually ~1 %): the kernel reads
@@ -402,12 +406,20 @@ void launch_knn(QueryTree const &qt, QueryBatch const &qb, DeferList defer, CdfA
             return;
         }
     }
+    // NBK_CDF_KEYS=64: the fused kNN-CDF keeps (d2, index) keys in its first pass too (the previous form)
+    static const bool dist_only_cdf = [] {
+        const char *v = std::getenv("NBK_CDF_KEYS");
+        return !(v && std::string(v) == "64");
+    }();
+    const bool dist_only = cdf.edges != nullptr && dist_only_cdf;
     if constexpr (K == 0) {
-        launch_lane<HeapT<0>, P>(qt, qb, defer, cdf, stream);
+        launch_lane<HeapT<0>, HeapT<0>, P>(qt, qb, defer, cdf, stream);
     } else if constexpr (K >= 16) {
-        launch_lane<HeapT<K>, P>(qt, qb, defer, cdf, stream);
+        if (dist_only) launch_lane<DistHeapT<K>, HeapT<K>, P>(qt, qb, defer, cdf, stream);
+        else launch_lane<HeapT<K>, HeapT<K>, P>(qt, qb, defer, cdf, stream);
     } else {
-        launch_lane<TopK<K>, P>(qt, qb, defer, cdf, stream);
+        if (dist_only) launch_lane<DistTopK<K>, TopK<K>, P>(qt, qb, defer, cdf, stream);
+        else launch_lane<TopK<K>, TopK<K>, P>(qt, qb, defer, cdf, stream);
     }
 }
 
@@ -430,7 +442,7 @@ void dispatch_knn(QueryTree const &qt, QueryBatch const &qb, DeferList defer, Cd
 
 template <typename Top, bool P>
 void launch_scan_block(QueryTree const &qt, uint32_t n, QueryBatch const &qb, cudaStream_t stream) {
-    size_t smem = Top::kShared ? (size_t)Top::kSize * kQueryThreads * sizeof(unsigned long long) : 0;
+    size_t smem = Top::kShared ? (size_t)Top::kSize * kQueryThreads * Top::kKeyBytes : 0;
     auto kern = scan_block_kernel<Top, P>;
     if (smem > 48 * 1024) NBK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)div_up(qb.m, kQueryThreads), kQueryThreads, smem, stream>>>(qt, n, qb);
