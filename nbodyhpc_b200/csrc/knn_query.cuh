@@ -527,6 +527,9 @@ __device__ __forceinline__ void scan_leaf(QueryTree const &t, uint32_t begin, ui
 #define NBK_QUEUE_CAP 0 // 0: insert inside the scan loop (no queue)
 #endif
 constexpr int kQueueCap = NBK_QUEUE_CAP;
+#ifndef NBK_QUEUE_HOME
+#define NBK_QUEUE_HOME 1 // 0: the home-leaf round inserts directly, only the later leaves are queued
+#endif
 
 struct CandQueue { // slot-major like the heaps: queue[slot * blockDim + thread]
     unsigned long long *col;
@@ -903,7 +906,13 @@ __device__ __forceinline__ void lane_query(QueryTree const &t, QueryBatch const 
                 scan_leaf<Top, PERIODIC>(t, lbeg, lend, qx, qy, qz, wrap_d2, false, k, top);
             }
         } else if (kQueued) {
+#if NBK_QUEUE_HOME
             scan_leaf_queued<Top, PERIODIC>(t, lbeg, lend, qx, qy, qz, wrap_d2, IMAGES && img > 0, first_round, k, top, cq);
+#else
+            // home-leaf round: direct insertion (its insertion sites are busy anyway); queue + drain afterwards
+            if (first_round) scan_leaf<Top, PERIODIC>(t, lbeg, lend, qx, qy, qz, wrap_d2, false, k, top);
+            else scan_leaf_queued<Top, PERIODIC>(t, lbeg, lend, qx, qy, qz, wrap_d2, IMAGES && img > 0, false, k, top, cq);
+#endif
             first_round = false;
         } else {
             scan_leaf<Top, PERIODIC>(t, lbeg, lend, qx, qy, qz, wrap_d2, IMAGES && img > 0, k, top);
