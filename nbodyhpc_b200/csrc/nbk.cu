@@ -859,7 +859,10 @@ int nbk_tree_query_ex2(const nbk_tree *tree, const float *q_aos, uint64_t m, int
         }();
         std::unique_ptr<StagedDownload> staged;
         PinnedRing *staged_ring = nullptr;
-        if (m * (uint64_t)k * 8 >= (64u << 20) && is_pageable_host(out_dist) && is_pageable_host(out_idx)) {
+        // (decided per array: one of the two may be a recycled, page-locked buffer while the other is fresh)
+        const bool big_rows = m * (uint64_t)k * 8 >= (64u << 20);
+        const bool stage_dist = big_rows && is_pageable_host(out_dist), stage_idx = big_rows && is_pageable_host(out_idx);
+        if (stage_dist || stage_idx) {
             if ((staged_ring = PinnedRing::acquire(tree->device))) {
                 try {
                     staged = std::make_unique<StagedDownload>(staged_ring, tree->device, host_threads);
@@ -885,13 +888,10 @@ int nbk_tree_query_ex2(const nbk_tree *tree, const float *q_aos, uint64_t m, int
         if (upload_ring) uploader = std::make_unique<StagedUpload>(upload_ring, tree->device, std::max(2, host_threads / 2));
         auto download = [&](int s, uint64_t begin, uint64_t cnt) {
             const uint64_t bytes = cnt * (uint64_t)k * 4;
-            if (staged) {
-                staged->download(out_dist + begin * k, d_d[s], bytes, streams[s]);
-                staged->download(out_idx + begin * k, d_i[s], bytes, streams[s]);
-            } else {
-                NBK_CUDA(cudaMemcpyAsync(out_dist + begin * k, d_d[s], bytes, cudaMemcpyDeviceToHost, streams[s]));
-                NBK_CUDA(cudaMemcpyAsync(out_idx + begin * k, d_i[s], bytes, cudaMemcpyDeviceToHost, streams[s]));
-            }
+            if (staged && stage_dist) staged->download(out_dist + begin * k, d_d[s], bytes, streams[s]);
+            else NBK_CUDA(cudaMemcpyAsync(out_dist + begin * k, d_d[s], bytes, cudaMemcpyDeviceToHost, streams[s]));
+            if (staged && stage_idx) staged->download(out_idx + begin * k, d_i[s], bytes, streams[s]);
+            else NBK_CUDA(cudaMemcpyAsync(out_idx + begin * k, d_i[s], bytes, cudaMemcpyDeviceToHost, streams[s]));
         };
         try {
             for (int s = 0; s < nbuf; ++s) {
