@@ -52,6 +52,7 @@ struct BlockCache {
         uint64_t bytes;
         int device;
         bool busy;
+        cudaEvent_t ready; // work still reading the block when it was released (a freed tree's queries), or null
     };
     static std::mutex &mutex() {
         static std::mutex m;
@@ -61,7 +62,8 @@ struct BlockCache {
         static std::vector<Entry> e;
         return e;
     }
-    static void *acquire(uint64_t bytes) {
+    // `stream`: where the caller will first use the block (made to wait for the block's previous readers)
+    static void *acquire(uint64_t bytes, cudaStream_t stream) {
         int dev = 0;
         NBK_CUDA(cudaGetDevice(&dev));
         std::lock_guard<std::mutex> lock(mutex());
@@ -73,6 +75,11 @@ struct BlockCache {
                 best = &e;
         if (best) {
             best->busy = true;
+            if (best->ready) {
+                cudaStreamWaitEvent(stream, best->ready, 0);
+                cudaEventDestroy(best->ready);
+                best->ready = nullptr;
+            }
             return best->ptr;
         }
         // miss: if the cache is full of wrong-sized idle blocks, drop them, then take a fresh one
@@ -81,7 +88,7 @@ struct BlockCache {
         if (idle >= 4) {
             for (size_t i = 0; i < es.size();) {
                 if (!es[i].busy && es[i].device == dev) {
-                    cudaFree(es[i].ptr);
+                    drop(es[i]);
                     es.erase(es.begin() + i);
                 } else {
                     ++i;
@@ -95,7 +102,7 @@ struct BlockCache {
             cudaGetLastError();
             for (size_t i = 0; i < es.size();) {
                 if (!es[i].busy && es[i].device == dev) {
-                    cudaFree(es[i].ptr);
+                    drop(es[i]);
                     es.erase(es.begin() + i);
                 } else {
                     ++i;
@@ -103,20 +110,31 @@ struct BlockCache {
             }
             NBK_CUDA(cudaMalloc(&p, bytes));
         }
-        es.push_back(Entry{p, bytes, dev, true});
+        es.push_back(Entry{p, bytes, dev, true, nullptr});
         return p;
     }
-    static void release(void *ptr) {
+    // `ready` (optional, ownership passes to the cache): an event after which the block is no longer read
+    static void release(void *ptr, cudaEvent_t ready = nullptr) {
         std::lock_guard<std::mutex> lock(mutex());
         for (auto &e : entries())
-            if (e.ptr == ptr) e.busy = false;
+            if (e.ptr == ptr) {
+                e.busy = false;
+                e.ready = ready;
+                return;
+            }
+        if (ready) cudaEventDestroy(ready);
+    }
+    static void drop(Entry &e) { // cudaFree waits for the device, so a pending `ready` is settled by it
+        if (e.ready) cudaEventDestroy(e.ready);
+        e.ready = nullptr;
+        cudaFree(e.ptr);
     }
     static void trim(int device) {
         std::lock_guard<std::mutex> lock(mutex());
         auto &es = entries();
         for (size_t i = 0; i < es.size();) {
             if (!es[i].busy && es[i].device == device) {
-                cudaFree(es[i].ptr);
+                drop(es[i]);
                 es.erase(es.begin() + i);
             } else {
                 ++i;
@@ -143,7 +161,7 @@ struct Scratch {
     void reserve(uint64_t bytes) {
         if (block || bytes == 0) return;
         if (bytes >= kCacheFrom) {
-            block = static_cast<char *>(BlockCache::acquire(bytes));
+            block = static_cast<char *>(BlockCache::acquire(bytes, stream));
             block_cached = true;
         } else {
             void *p = nullptr;
