@@ -761,7 +761,9 @@ template <typename Top, bool PERIODIC, bool IMAGES>
 __device__ __forceinline__ void lane_query(QueryTree const &t, QueryBatch const &a, DeferList const &defer,
                                            CdfArgs const &cdf, Top &top, uint64_t slot, bool valid,
                                            StageBuf const &stage = StageBuf{nullptr, 0u}) {
-    const uint32_t qid = a.order[valid ? slot : a.m - 1];
+    // (tiny batches are not ordered: order == null means slot == query id)
+    const uint64_t safe_slot = valid ? slot : a.m - 1;
+    const uint32_t qid = a.order ? a.order[safe_slot] : (uint32_t)safe_slot;
     const float qx = a.q_aos[3 * (uint64_t)qid], qy = a.q_aos[3 * (uint64_t)qid + 1],
                 qz = a.q_aos[3 * (uint64_t)qid + 2];
     const float L = t.box;

@@ -525,35 +525,43 @@ void query_device(nbk_tree const &tree, const float *d_q, uint64_t m, int k, flo
     }();
     const int passes = (30 - first_bit + 7) / 8;
     const bool use_sweep = sweep && m < (1ull << 30); // the look-back words hold 30-bit counts
+    // a handful of warps gain nothing from an ordering that costs six launches: find_closest (m = 1) and
+    // other tiny batches go straight to the kernel
+    const bool ordered = m > 4096 || use_packet_kernel();
     Scratch scratch(stream);
-    uint32_t *keys_a = scratch.get<uint32_t>(m), *keys_b = scratch.get<uint32_t>(m);
-    uint32_t *vals_a = scratch.get<uint32_t>(m), *vals_b = scratch.get<uint32_t>(m);
-    uint32_t *work = scratch.get<uint32_t>(use_sweep ? rs::sweep_workspace_entries(m, passes)
-                                                 : rs::sort_workspace_entries<uint32_t>(m));
+    uint32_t *keys_a = scratch.get<uint32_t>(m), *keys_b = nullptr, *vals_a = nullptr, *vals_b = nullptr;
+    const uint32_t *order = nullptr;
+    int where = 0;
     SectionTimer t_order(NBK_SECTION_QUERY_ORDER, stream);
-    int where;
-    if (use_sweep) {
-        rs::SweepWorkspace w = rs::sweep_workspace(work, m, passes, stream);
-        morton_keys_totals_kernel<<<(unsigned)div_up(m, kKeysPerCta), 256, 0, stream>>>(
-            d_q, m, lo[0], lo[1], lo[2], scale[0], scale[1], scale[2], first_bit, passes, keys_a, w.digit_totals);
-        NBK_LAUNCHED();
-        where = rs::sweep_order(keys_a, vals_a, keys_b, vals_b, m, first_bit, passes, w, stream);
-    } else {
-        morton_keys_kernel<<<(unsigned)div_up(m, 256), 256, 0, stream>>>(d_q, m, lo[0], lo[1], lo[2], scale[0],
-                                                                       scale[1], scale[2], keys_a, vals_a);
-        NBK_LAUNCHED();
+    if (ordered) {
+        keys_b = scratch.get<uint32_t>(m);
+        vals_a = scratch.get<uint32_t>(m);
+        vals_b = scratch.get<uint32_t>(m);
+        uint32_t *work = scratch.get<uint32_t>(use_sweep ? rs::sweep_workspace_entries(m, passes)
+                                                     : rs::sort_workspace_entries<uint32_t>(m));
+        if (use_sweep) {
+            rs::SweepWorkspace w = rs::sweep_workspace(work, m, passes, stream);
+            morton_keys_totals_kernel<<<(unsigned)div_up(m, kKeysPerCta), 256, 0, stream>>>(
+                d_q, m, lo[0], lo[1], lo[2], scale[0], scale[1], scale[2], first_bit, passes, keys_a, w.digit_totals);
+            NBK_LAUNCHED();
+            where = rs::sweep_order(keys_a, vals_a, keys_b, vals_b, m, first_bit, passes, w, stream);
+        } else {
+            morton_keys_kernel<<<(unsigned)div_up(m, 256), 256, 0, stream>>>(d_q, m, lo[0], lo[1], lo[2], scale[0],
+                                                                           scale[1], scale[2], keys_a, vals_a);
+            NBK_LAUNCHED();
 #ifndef NBK_SORT_STABLE
 #define NBK_SORT_STABLE 0
 #endif
-        where = rs::sort_pairs<uint32_t, NBK_SORT_STABLE != 0>(keys_a, vals_a, keys_b, vals_b, m, first_bit, 30, work, stream);
+            where = rs::sort_pairs<uint32_t, NBK_SORT_STABLE != 0>(keys_a, vals_a, keys_b, vals_b, m, first_bit, 30, work, stream);
+        }
+        order = where ? vals_b : vals_a;
     }
-    const uint32_t *order = where ? vals_b : vals_a;
     t_order.finish();
     SectionTimer t_knn(NBK_SECTION_KNN_KERNEL, stream);
     DeferList defer{nullptr, nullptr};
     if (qt.periodic && !use_packet_kernel()) {
         // the sort's input buffers are free again: reuse one as the deferred-query list
-        defer.slots = where ? keys_a : keys_b;
+        defer.slots = (ordered && !where) ? keys_b : keys_a;
         defer.count = scratch.get<uint32_t>(2);
     }
     QueryBatch qb{d_q, order, m, k, flags, d_out_d, d_out_i, nullptr, 0u};
