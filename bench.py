@@ -103,7 +103,15 @@ def ncu_traffic(args):
             and rec.get("k") == args.k and rec.get("leaf") == args.leaf)
     if not same:
         return None, "ncu capture is for another workload"
-    return rec["dram_bytes_per_launch"], rec.get("source", path)
+    # the capture names the kernel source it was taken from: say so when the kernels have changed since
+    import hashlib
+
+    with open(os.path.join(ROOT, "nbodyhpc_b200", "csrc", "knn_query.cuh"), "rb") as f:
+        current = hashlib.sha1(f.read()).hexdigest()
+    note = rec.get("source", path)
+    if rec.get("kernel_source_sha1") != current:
+        note = "STALE (knn_query.cuh changed since the capture; rerun scripts/refresh_traffic.py): " + note
+    return rec["dram_bytes_per_launch"], note
 
 
 def measured_hbm_peak():
