@@ -181,7 +181,7 @@ NBK_API int nbk_tree_stats(const nbk_tree *tree, const float *q_aos, uint64_t m,
 
 /* ---- replication (one process per GPU; the bytes move with an NCCL broadcast) -------------- */
 
-/* Device address of the packed arena [nodes | x | y | z | idx] (meta.arena_bytes bytes). */
+/* Device address of the packed arena [nodes | 128-byte point tiles] (meta.arena_bytes bytes). */
 NBK_API int nbk_tree_arena(const nbk_tree *tree, void **d_arena, uint64_t *bytes);
 
 /* Allocates an empty tree with the given meta on `device`; the caller fills its arena (e.g. as the

@@ -42,7 +42,7 @@ class _DeviceBytes:
 
 
 def arena_tensor(tree: capi.Tree):
-    """uint8 torch view of the tree's packed arena [nodes | x | y | z | idx] (no copy)."""
+    """uint8 torch view of the tree's packed arena [nodes | 128-byte point tiles] (no copy)."""
     import torch
 
     ptr, nbytes = tree.arena()
