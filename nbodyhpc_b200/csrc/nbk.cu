@@ -846,6 +846,20 @@ int nbk_tree_query_ex2(const nbk_tree *tree, const float *q_aos, uint64_t m, int
         if (flags & ~NBK_QUERY_SQUARED) throw Error(NBK_ERR_INVALID, "unknown query flag");
         if (m == 0) return;
         DeviceGuard guard(tree->device);
+        if (m <= 4096) {
+            // find_closest and other tiny batches: no pipeline to set up, one round trip on the calling
+            // thread's own stream
+            cudaStream_t st = cudaStreamPerThread;
+            Scratch scratch(st);
+            float *dq = scratch.get<float>(m * 3), *dd = scratch.get<float>(m * (uint64_t)k);
+            uint32_t *di = scratch.get<uint32_t>(m * (uint64_t)k);
+            NBK_CUDA(cudaMemcpyAsync(dq, q_aos, m * 12, cudaMemcpyHostToDevice, st));
+            query_device(*tree, dq, m, k, dd, di, st, periodic, box_size, CdfArgs{nullptr, nullptr, nullptr, 0}, flags);
+            NBK_CUDA(cudaMemcpyAsync(out_dist, dd, m * (uint64_t)k * 4, cudaMemcpyDeviceToHost, st));
+            NBK_CUDA(cudaMemcpyAsync(out_idx, di, m * (uint64_t)k * 4, cudaMemcpyDeviceToHost, st));
+            NBK_CUDA(cudaStreamSynchronize(st));
+            return;
+        }
         // Up to three slices in flight, one stream each: slice c+2 uploads while slice c+1 computes
         // and slice c downloads.  A slice is ordered (Morton sort) on its own, and the kernel gets slower
         // per query as slices get smaller (fewer queries per leaf), but the pipeline is bound by the copies
