@@ -227,3 +227,37 @@ def test_python_result_buffers_are_recycled_pinned(gpu):
     # results still referenced are never touched by later calls
     d2, i2 = tree.query(q, k=8)
     assert d2.ctypes.data != d.ctypes.data and np.array_equal(d2, d) and np.array_equal(d, keep_d)
+
+
+def test_packet_kernel_still_agrees(gpu, tmp_path):
+    """NBK_KERNEL=packet (the first design: one traversal per warp, kept as the measured alternative) must
+    keep giving the rows of the default kernel."""
+    import os
+    import subprocess
+    import sys
+
+    pts, q = philox(60_000, 42), philox(6_000, 43)
+    np.save(tmp_path / "pts.npy", pts)
+    np.save(tmp_path / "q.npy", q)
+    script = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "from nbodyhpc_b200 import capi\n"
+        "pts, q = np.load(%r), np.load(%r)\n"
+        "out = {}\n"
+        "for box in (None, 1.0):\n"
+        "    t = capi.Tree.build(pts, 64, box)\n"
+        "    for k in (1, 3, 8):\n"
+        "        d, i = t.query(q, k, squared=(k == 3))\n"
+        "        out[f'd{k}{box}'] = d; out[f'i{k}{box}'] = i\n"
+        "np.savez(%r, **out)\n"
+    )
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for mode in ("lane", "packet"):
+        dst = str(tmp_path / f"{mode}.npz")
+        env = dict(os.environ, NBK_KERNEL=mode)
+        subprocess.run([sys.executable, "-c", script % (root, str(tmp_path / "pts.npy"), str(tmp_path / "q.npy"), dst)],
+                       check=True, env=env, timeout=180)
+        res[mode] = np.load(dst)
+    for key in res["lane"].files:
+        assert np.array_equal(res["lane"][key], res["packet"][key]), key
