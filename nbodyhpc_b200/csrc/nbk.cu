@@ -559,7 +559,7 @@ void query_device(nbk_tree const &tree, const float *d_q, uint64_t m, int k, flo
     t_order.finish();
     SectionTimer t_knn(NBK_SECTION_KNN_KERNEL, stream);
     DeferList defer{nullptr, nullptr};
-    if (qt.periodic && !use_packet_kernel()) {
+    if (qt.periodic) { // (the packet kernel ignores it, but k > 8 falls through to the lane kernels even then)
         // the sort's input buffers are free again: reuse one as the deferred-query list
         defer.slots = (ordered && !where) ? keys_b : keys_a;
         defer.count = scratch.get<uint32_t>(2);

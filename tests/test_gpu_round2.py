@@ -229,35 +229,44 @@ def test_python_result_buffers_are_recycled_pinned(gpu):
     assert d2.ctypes.data != d.ctypes.data and np.array_equal(d2, d) and np.array_equal(d, keep_d)
 
 
-def test_packet_kernel_still_agrees(gpu, tmp_path):
-    """NBK_KERNEL=packet (the first design: one traversal per warp, kept as the measured alternative) must
-    keep giving the rows of the default kernel."""
+@pytest.mark.parametrize("variant", [{"NBK_KERNEL": "packet"}, {"NBK_ORDER": "passes"}, {"NBK_MAX_SHARED_K": "8"},
+                                     {"NBK_CDF_KEYS": "64"}, {"NBK_MORTON_FIRST_BIT": "0"}])
+def test_runtime_selected_alternatives_agree(gpu, tmp_path, variant):
+    """The alternatives kept behind environment switches (the packet kernel, the three-kernel ordering passes,
+    the global-memory heap for k > 8, (d2, index) keys in the CDF's first pass, a 30-bit Morton order) must
+    keep giving the rows and histograms of the defaults."""
     import os
     import subprocess
     import sys
 
-    pts, q = philox(60_000, 42), philox(6_000, 43)
+    pts, q = philox(60_000, 42), philox(9_000, 43)
     np.save(tmp_path / "pts.npy", pts)
     np.save(tmp_path / "q.npy", q)
     script = (
         "import sys, numpy as np; sys.path.insert(0, %r)\n"
         "from nbodyhpc_b200 import capi\n"
         "pts, q = np.load(%r), np.load(%r)\n"
+        "edges = np.linspace(0, 0.2, 25).astype(np.float32)\n"
         "out = {}\n"
         "for box in (None, 1.0):\n"
         "    t = capi.Tree.build(pts, 64, box)\n"
-        "    for k in (1, 3, 8):\n"
+        "    for k in (1, 3, 8, 16):\n"
         "        d, i = t.query(q, k, squared=(k == 3))\n"
         "        out[f'd{k}{box}'] = d; out[f'i{k}{box}'] = i\n"
+        "    if %r: out[f'cdf{box}'] = t.knn_cdf(q, [2, 8, 16], edges)\n"
         "np.savez(%r, **out)\n"
     )
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = {}
-    for mode in ("lane", "packet"):
+    for mode, extra in (("default", {}), ("variant", variant)):
         dst = str(tmp_path / f"{mode}.npz")
-        env = dict(os.environ, NBK_KERNEL=mode)
-        subprocess.run([sys.executable, "-c", script % (root, str(tmp_path / "pts.npy"), str(tmp_path / "q.npy"), dst)],
+        env = {k: v for k, v in os.environ.items() if not k.startswith("NBK_")}
+        env.update(extra)
+        with_cdf = "NBK_KERNEL" not in variant  # the packet kernel has no CDF epilogue (it says so)
+        subprocess.run([sys.executable, "-c",
+                        script % (root, str(tmp_path / "pts.npy"), str(tmp_path / "q.npy"), with_cdf, dst)],
                        check=True, env=env, timeout=180)
         res[mode] = np.load(dst)
-    for key in res["lane"].files:
-        assert np.array_equal(res["lane"][key], res["packet"][key]), key
+    assert len(res["default"].files) >= 16
+    for key in res["default"].files:
+        assert np.array_equal(res["default"][key], res["variant"][key]), (variant, key)
