@@ -247,13 +247,20 @@ scatter_kernel(const KeyT *__restrict__ kin, const uint32_t *__restrict__ vin,
 // atomics (see STABLE = false above).  FIRST: the payload is the position itself (not read);
 // LAST: only the payload is written.
 constexpr uint32_t kStateAggregate = 1u << 30, kStatePrefix = 2u << 30, kStateCount = (1u << 30) - 1u;
-constexpr int kSweepItems = 16;
+#ifndef NBK_SWEEP_ITEMS
+#define NBK_SWEEP_ITEMS 16
+#endif
+#ifndef NBK_SWEEP_MIN_BLOCKS
+#define NBK_SWEEP_MIN_BLOCKS 4 // 64 registers: the pass is bound by load latency (ncu: 24 resident warps at 80 registers,
+#endif                         // long-scoreboard stalls 5.4 per issue); measured 2.33 -> 2.17 ms per 10^8 queries; 8 or 12
+                               // keys per thread instead of 16: 3.57 / 3.19 ms
+constexpr int kSweepItems = NBK_SWEEP_ITEMS;
 constexpr int kSweepTile = kThreads * kSweepItems;
 
 inline uint64_t sweep_tiles(uint64_t n) { return div_up(n, (uint64_t)kSweepTile); }
 
 template <bool FIRST, bool LAST>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, NBK_SWEEP_MIN_BLOCKS)
 sweep_kernel(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, uint32_t *__restrict__ kout,
              uint32_t *__restrict__ vout, uint64_t n, int shift, const uint32_t *__restrict__ digit_totals,
              uint32_t *state, uint32_t *ticket) {
