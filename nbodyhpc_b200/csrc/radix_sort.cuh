@@ -296,20 +296,38 @@ sweep_kernel(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin,
         r[it] = i < n ? atomicAdd(&wh[(k[it] >> shift) & (kRadix - 1)], 1u) : 0u;
     }
     __syncthreads();
-    {
-        // thread t owns digit t
-        uint32_t total = 0;
+    // thread t owns digit t
+    uint32_t total = 0;
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-            const uint32_t c = whist[w * kRadix + threadIdx.x];
-            whist[w * kRadix + threadIdx.x] = total;
-            total += c;
+    for (int w = 0; w < kWarps; ++w) {
+        const uint32_t c = whist[w * kRadix + threadIdx.x];
+        whist[w * kRadix + threadIdx.x] = total;
+        total += c;
+    }
+    volatile uint32_t *st = state;
+    st[(uint64_t)tile * kRadix + threadIdx.x] = total | kStateAggregate; // published before anything is waited for
+    // global start of the digit = digits below it (all tiles) + this digit in earlier tiles
+    uint32_t all_tiles;
+    const uint32_t below = block_exclusive_scan(digit_totals[threadIdx.x], warp_sums, all_tiles);
+    {
+        uint32_t tile_total;
+        const uint32_t start = block_exclusive_scan(total, warp_sums, tile_total);
+        dstart[threadIdx.x] = start;
+    }
+    __syncthreads();
+    // the tile is brought into digit order in shared memory first: by the time the look-back starts, the
+    // earlier tiles have had that long to publish their counts
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+        const uint64_t i = warp_base + it * 32 + lane;
+        if (i < n) {
+            const uint32_t d = (k[it] >> shift) & (kRadix - 1);
+            const uint32_t pos = dstart[d] + wh[d] + r[it];
+            skeys[pos] = k[it];
+            svals[pos] = v[it];
         }
-        volatile uint32_t *st = state;
-        st[(uint64_t)tile * kRadix + threadIdx.x] = total | kStateAggregate;
-        // global start of the digit = digits below it (all tiles) + this digit in earlier tiles
-        uint32_t all_tiles;
-        const uint32_t below = block_exclusive_scan(digit_totals[threadIdx.x], warp_sums, all_tiles);
+    }
+    {
         uint32_t earlier = 0;
         for (int64_t prev = (int64_t)tile - 1; prev >= 0; --prev) {
             uint32_t seen, spins = 0;
@@ -320,20 +338,6 @@ sweep_kernel(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin,
         }
         st[(uint64_t)tile * kRadix + threadIdx.x] = ((earlier + total) & kStateCount) | kStatePrefix;
         gofs[threadIdx.x] = below + earlier;
-        uint32_t tile_total;
-        const uint32_t start = block_exclusive_scan(total, warp_sums, tile_total);
-        dstart[threadIdx.x] = start;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int it = 0; it < ITEMS; ++it) {
-        const uint64_t i = warp_base + it * 32 + lane;
-        if (i < n) {
-            const uint32_t d = (k[it] >> shift) & (kRadix - 1);
-            const uint32_t pos = dstart[d] + wh[d] + r[it];
-            skeys[pos] = k[it];
-            svals[pos] = v[it];
-        }
     }
     __syncthreads();
     const uint64_t remaining = n - tile_base;
